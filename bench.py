@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- fused fake-quant forward + threshold backward throughput on B200.
+
+Workload (BASELINE.json configs[3] at its headline size): one fp32 tensor of 64 Mi elements,
+per-channel scales, layout [outer, C, inner] = [256, 512, 512]; a "step" is one forward
+(lq_fq_fwd, 8 B/elem) plus one nested backward (lq_fq_bwd_threshold writing dX, 12 B/elem)
+over the whole tensor.  metric = 20 * N / t in GB/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fakequant_fwd_bwd_GBps"
+UNIT = "GB/s"
+LAYOUT = (256, 512, 512)          # 64 Mi elements, channelwise C = 512 on an HWIO-like tensor
+LAMBDA = 1e-3                     # ~3% of elements below threshold: both NQ:103-111 branches live
+BYTES_FWD, BYTES_BWD = 8, 12      # algorithmic bytes per element (SURVEY 8d / BASELINE.md 3)
+
+
+def synth(layout, seed, numpy=False):
+    """P ~ N(0, 0.05^2), s ~ U[5e-3, 2e-2], dy ~ N(0, 1e-3^2)  (BASELINE.md section 5)."""
+    import numpy as np
+    n = layout[0] * layout[1] * layout[2]
+    rng = np.random.default_rng(seed)
+    P = rng.standard_normal(n, dtype=np.float32) * np.float32(0.05)
+    dy = rng.standard_normal(n, dtype=np.float32) * np.float32(1e-3)
+    s = rng.uniform(5e-3, 2e-2, size=layout[1]).astype(np.float32)
+    return P, s, dy
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(names, r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------- CPU arms
+def cpu_oracle_step(P, s, dy, layout, lam):
+    """One fwd+bwd of the oracle port (oracle/lq_oracle.py, un-fused op chain like NQ:55-118)."""
+    from oracle import lq_oracle as o
+    shape = layout
+    q, y = o.fq_forward(P.reshape(shape), s.reshape(1, layout[1], 1))
+    _, ds = o.nested_backward(dy.reshape(shape), q, y, s.reshape(1, layout[1], 1), lam)
+    return y, ds
+
+
+def cpu_baseline(sample_outer, reps=1):
+    layout = (sample_outer, LAYOUT[1], LAYOUT[2])
+    P, s, dy = synth(layout, 42)
+    n = P.size
+    cpu_oracle_step(P[: n // 8], s, dy[: n // 8], (max(sample_outer // 8, 1), layout[1], layout[2]), LAMBDA)  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (BYTES_FWD + BYTES_BWD) * n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle/lq_oracle.py (numpy, single thread) fwd+bwd on [{layout[0]},{layout[1]},{layout[2]}] "
+                      f"= {n} elements of the workload, {dt:.2f} s",
+            "host_cpus": os.cpu_count()}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_outer = 8      # 2 Mi elements per step
+    cb, _ = cpu_baseline(sample_outer)
+    layout = (sample_outer, LAYOUT[1], LAYOUT[2])
+    P, s, dy = synth(layout, 42)
+    for _ in range(args.warmup):
+        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+    dt = time.perf_counter() - t0
+    val = (BYTES_FWD + BYTES_BWD) * P.size * args.steps / dt / 1e9
+    cb["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fakequant_fwd_bwd_channelwise_C512_inner512", "layout": list(LAYOUT),
+                   "lambda": LAMBDA, "step": f"bounded sample [{sample_outer},512,512] of the 64Mi-element tensor",
+                   "note": "reference CPU path = TensorFlow-CPU (not installable); timed stand-in is the op-for-op oracle port"},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import learned_quantization_b200 as lq
+    ops = lq.ops
+
+    n = LAYOUT[0] * LAYOUT[1] * LAYOUT[2]
+    P_h, s_h, dy_h = synth(LAYOUT, 42 + rank)
+    # two input sets, alternated between steps; each array is 256 MiB (> 126 MB L2)
+    sets = []
+    for k in range(2):
+        P = torch.from_numpy(P_h).cuda() if k == 0 else torch.from_numpy(P_h).cuda().roll(4099)
+        dy = torch.from_numpy(dy_h).cuda() if k == 0 else torch.from_numpy(dy_h).cuda().roll(977)
+        sets.append((P, dy))
+    s = torch.from_numpy(s_h).cuda()
+    y = torch.empty(n, device="cuda")
+    dX = torch.empty(n, device="cuda")
+    ds = torch.empty(LAYOUT[1], device="cuda")
+    d = ops.make_desc(layout=LAYOUT)
+    ws = torch.empty(ops.workspace_bytes([d], lq._lib.LQ_PHASE_BWD), dtype=torch.uint8, device="cuda")
+    lib, check = lq._lib.lib, lq._lib.check
+    stream = torch.cuda.current_stream().cuda_stream
+    ninf, pinf = float("-inf"), float("inf")
+
+    def fwd(P):
+        check(lib.lq_fq_fwd(P.data_ptr(), s.data_ptr(), y.data_ptr(), None, 0, *LAYOUT, 0, ninf, pinf, stream))
+
+    def bwd(P, dy):
+        check(lib.lq_fq_bwd_threshold(dy.data_ptr(), P.data_ptr(), s.data_ptr(), LAMBDA, dX.data_ptr(), ds.data_ptr(),
+                                      *LAYOUT, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        P, dy = sets[i % 2]
+        fwd(P); bwd(P, dy)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        P, dy = sets[i % 2]
+        ev[i][0].record()
+        fwd(P)
+        ev[i][1].record()
+        bwd(P, dy)
+        ev[i][2].record()
+    barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+
+    # ---- end to end through the host-buffer C-ABI entry (pinned host arrays in, host arrays out)
+    hP, hs, hdy = (torch.from_numpy(a).pin_memory() for a in (P_h, s_h, dy_h))
+    hy = torch.empty(n).pin_memory()
+    hds = torch.empty(LAYOUT[1]).pin_memory()
+    hws = torch.empty(ops.host_workspace_bytes(LAYOUT), dtype=torch.uint8, device="cuda")
+    e2e_steps = max(3, min(args.steps, 10))
+    ops.host_fq_fwd_bwd(hP, hs, hdy, LAMBDA, hy, hds, LAYOUT, hws)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.host_fq_fwd_bwd(hP, hs, hdy, LAMBDA, hy, hds, LAYOUT, hws)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_ms, fwd_ms, bwd_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fwd_ms, bwd_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        step_ms = total_ms / args.steps
+        value = (BYTES_FWD + BYTES_BWD) * n * world / (step_ms * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        achieved = BYTES_BWD * n / (bwd_ms * 1e-3) / 1e9
+        cb, _ = cpu_baseline(32) if world == 1 else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fakequant_fwd_bwd_channelwise_C512_inner512", "layout": list(LAYOUT),
+                       "elements_per_gpu": n, "lambda": LAMBDA, "l2": "inputs_exceed_l2 (3 x 256 MiB arrays per pass, 2 input sets alternated)",
+                       "bytes_per_element": {"fwd": BYTES_FWD, "bwd": BYTES_BWD}, "dX": "written (not aliased to dy)"},
+            "elements_per_s": n * world / (step_ms * 1e-3),
+            "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_kernel, 512 blocks)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": None},
+            "e2e": {"value": (BYTES_FWD + BYTES_BWD) * n * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n + 4 * LAYOUT[1],
+                    "d2h_bytes_per_step": 4 * n + 4 * LAYOUT[1],
+                    "api": "lq_host_fq_fwd_bwd (pinned host P, s, dy in; host y, ds out; dX is dy itself)"},
+            "gpu_launches": 3 * args.steps,
+            "clocks": clocks,
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/* lq.h -- C ABI of liblq.so: the B200 (sm_100a) learned-quantization hot path.
+ *
+ * Drop-in boundary for the operator the reference implements in TensorFlow as
+ *   @tf.custom_gradient my_custom_gradient(parameter, scale[, penalty_threshold])
+ * (IMAGENETTE/nested_quantization_layer/custom_components/custom_layers.py:49-120,
+ *  IMAGENETTE/custom_loss_terms/custom_components/custom_layers.py:49-64,
+ *  CIFAR-10/paper_implementation/custom_components/custom_layers.py:49-66)
+ * and for the penalty reductions of
+ *  IMAGENETTE/custom_loss_terms/custom_components/custom_loss_functions.py:75-116,161-195,240-275.
+ * Paths are relative to the reference root; "NQ", "CL", "PI", "LF" below abbreviate them.
+ *
+ * Conventions
+ *  - Every tensor is contiguous fp32, viewed as [outer, C, inner] row-major with
+ *    group(idx) = (idx / inner) % C; `s` and `ds` hold C floats.  The four reference
+ *    orientations map onto this view (NQ:147-197; table in DESIGN.md).
+ *  - All pointers are DEVICE pointers on the current device unless the name says host.
+ *    The caller owns every buffer including the workspace; the library never allocates
+ *    device memory, never synchronises (except the *_host entry points, which say so)
+ *    and enqueues all work on the caller's stream.
+ *  - Every function returns LQ_OK or a negative lq_status; lq_last_error() gives the
+ *    thread-local message.  Nothing throws.  There is no CPU fallback: without a CUDA
+ *    device every compute entry point returns LQ_E_CUDA.
+ */
+#ifndef LQ_H_
+#define LQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQ_VERSION 100 /* 0.1.0 */
+
+typedef void* lq_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
+
+typedef enum lq_status {
+  LQ_OK = 0,
+  LQ_E_NULLPTR = -1,
+  LQ_E_BADSHAPE = -2,
+  LQ_E_BADMODE = -3,
+  LQ_E_WORKSPACE = -4,
+  LQ_E_CUDA = -5,
+  LQ_E_NCCL = -6
+} lq_status;
+
+/* NQ:59 uses tf.floor; RNE (+ clamp) is the extension BASELINE.json's wording asks for. */
+enum { LQ_ROUND_FLOOR = 0, LQ_ROUND_RNE = 1 };
+/* optional integer-code output of the forward (utils/log_scripts.py:74-79 exports int8) */
+enum { LQ_CODES_NONE = 0, LQ_CODES_F32 = 1, LQ_CODES_I32 = 2, LQ_CODES_I8 = 3 };
+/* which custom loss term (LF:75, LF:161, LF:240) */
+enum { LQ_PEN_MAXBIN = 0, LQ_PEN_DIFFERENCE = 1, LQ_PEN_INVERSE = 2 };
+/* scale-gradient rule of the backward: NQ:62-118 (threshold) or CL:61-62 / PI:62-64 (zeros) */
+enum { LQ_SGRAD_NONE = 0, LQ_SGRAD_THRESHOLD = 1 };
+/* phases for lq_workspace_bytes */
+enum { LQ_PHASE_FWD = 0, LQ_PHASE_BWD = 1, LQ_PHASE_PENALTY_FWD = 2, LQ_PHASE_PENALTY_BWD = 3 };
+/* lq_tensor_desc.flags */
+enum { LQ_F_ACCUM_DX = 1u, /* penalty bwd: dX += grad instead of dX = grad */
+       LQ_F_ACCUM_DS = 2u  /* penalty bwd: ds += grad instead of ds = grad */ };
+
+/* One quantised parameter tensor (a kernel, a weight matrix or a bias) with its scale. */
+typedef struct lq_tensor_desc {
+  const float* P;  /* parameter                       [outer*C*inner] */
+  const float* s;  /* learned scale                   [C]             */
+  float* y;        /* fake-quantised parameter (fwd)  [outer*C*inner] */
+  const float* dy; /* upstream gradient (bwd)         [outer*C*inner] */
+  float* dX;       /* parameter gradient (bwd); may equal dy or be NULL (dP is dy itself, NQ:118) */
+  float* ds;       /* scale gradient (bwd)            [C]             */
+  int64_t outer, C, inner;
+  uint32_t flags;
+  uint32_t reserved;
+} lq_tensor_desc;
+
+int lq_version(void);
+const char* lq_last_error(void);
+/* number of SMs of the current device (0 and LQ_E_CUDA through lq_last_error when there is none) */
+int lq_device_sm_count(void);
+
+/* Bytes of device workspace the given phase needs for these tensors (sum over descs,
+ * each 256-B aligned).  Pure host arithmetic: works without a GPU. */
+int lq_workspace_bytes(const lq_tensor_desc* descs, int n, int phase, size_t* out_bytes);
+
+/* a1 forward, NQ:55-60:  q = floor(P / s) (IEEE division), y = q * s.
+ * codes (nullable) receives q as f32 / i32 / i8 (i8 wraps like numpy .astype(int8)).
+ * round_mode/qmin/qmax: LQ_ROUND_FLOOR with -inf/+inf reproduces the reference. */
+int lq_fq_fwd(const float* P, const float* s, float* y, void* codes, int codes_dtype,
+              int64_t outer, int64_t C, int64_t inner, int round_mode, float qmin, float qmax,
+              lq_stream_t stream);
+
+/* a2 backward, NQ:62-118:  dX = dy (skipped when dX is NULL or == dy) and
+ * ds[g] = mean_g(e) * max_g|q|, e as in NQ:103-111, recomputing q,y from P,s in registers.
+ * One HBM pass + a deterministic second-stage reduce over block partials in `ws`. */
+int lq_fq_bwd_threshold(const float* dy, const float* P, const float* s, float penalty_threshold,
+                        float* dX, float* ds, int64_t outer, int64_t C, int64_t inner,
+                        int round_mode, float qmin, float qmax,
+                        void* ws, size_t ws_bytes, lq_stream_t stream);
+
+/* a3 backward, CL:61-62 / PI:62-64:  dX = dy (copy skipped when NULL or aliased), ds = 0. */
+int lq_fq_bwd_ste(const float* dy, float* dX, float* ds, int64_t n_elems, int64_t C,
+                  lq_stream_t stream);
+
+/* a5 MinValueConstraint, NQ:35-46:  s = max(s, min_value) in place. */
+int lq_scale_constraint(float* s, int64_t n, float min_value, lq_stream_t stream);
+
+/* a7-a9 loss terms over a list of tensors (LF iterates layers; a layer contributes its
+ * kernel and its bias as two descs).  out_penalty[0] = compute_*_penalty() (un-scaled by
+ * the penalty rate, LF:116 / LF:195 / LF:275). Uses desc fields P, s, outer, C, inner. */
+int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, float* out_penalty,
+                   void* ws, size_t ws_bytes, lq_stream_t stream);
+
+/* TF-autodiff gradients of `u * penalty` w.r.t. every P (into desc.dX) and every s (into
+ * desc.ds), u = upstream * (upstream_dev ? *upstream_dev : 1): the device scalar lets an
+ * autograd engine pass its incoming gradient without a host sync.  LQ_F_ACCUM_* flags
+ * select += .  Must be given the workspace that the matching lq_penalty_fwd call filled
+ * (it holds the per-group maxima / tie counts).  Inverse never touches dX. */
+int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, float upstream,
+                   const float* upstream_dev, void* ws, size_t ws_bytes, lq_stream_t stream);
+
+/* K5 multi-tensor forms: ONE launch per phase over all descs (the models quantise 4-42
+ * small tensors per step; per-tensor launches dominate there). */
+int lq_mt_fq_fwd(const lq_tensor_desc* descs, int n, int round_mode, float qmin, float qmax,
+                 lq_stream_t stream);
+int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_threshold, int scale_grad_mode,
+                 int round_mode, float qmin, float qmax,
+                 void* ws, size_t ws_bytes, lq_stream_t stream);
+
+/* Host-buffer entry point (the end-to-end path bench.py times): pinned or pageable HOST
+ * arrays in, HOST arrays out; chunks are staged through the caller's device workspace
+ * (>= lq_host_workspace_bytes) on internal streams, copies overlapped with the kernels.
+ * SYNCHRONISES before returning.  hdX may be NULL (dP is dy itself). */
+int lq_host_workspace_bytes(int64_t outer, int64_t C, int64_t inner, size_t* out_bytes);
+int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float* hdy, float penalty_threshold,
+                       float* hy, float* hdX, float* hds,
+                       int64_t outer, int64_t C, int64_t inner,
+                       void* dev_ws, size_t dev_ws_bytes);
+
+/* Data parallelism (new; the reference is single-device, experiment.py:774-788):
+ * one NCCL communicator per process, sum-allreduce of a flat fp32 gradient bucket scaled
+ * by `scale` (1/world) in the same call. */
+typedef struct lq_dp lq_dp_t;
+int lq_dp_unique_id(void* out_id128);                       /* 128-byte ncclUniqueId */
+int lq_dp_init(const void* id128, int rank, int world, lq_dp_t** out);
+int lq_dp_allreduce(lq_dp_t* dp, float* flat, int64_t n, float scale, lq_stream_t stream);
+int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_stream_t stream);
+int lq_dp_destroy(lq_dp_t* dp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQ_H_ */

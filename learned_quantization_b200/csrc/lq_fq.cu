@@ -1,0 +1,298 @@
+// lq_fq.cu -- fake-quant forward (K1), threshold backward (K2), second-stage reduce (K4)
+// and their multi-tensor forms (K5).  Reference semantics: NQ:49-120 (see include/lq.h).
+#include <math.h>
+#include "lq_traverse.cuh"
+
+namespace lq {
+
+// ------------------------------------------------------------------ element operators
+// K1  NQ:55-60   y = floor(P / s) * s
+template <bool EXT>
+struct FwdOp {
+  QMode qm;
+  static constexpr bool kIn2 = false, kOutIsY = true, kCodes = true, kReduce = false, kAux = false;
+  __device__ static void init(Acc&) {}
+  __device__ static void combine(Acc&, const Acc&) {}
+  __device__ __forceinline__ void elem(float p, float, float s, const float4&, const Job&, Acc&, float& y, float& q) const {
+    q = quant_code<EXT>(p, s, qm);
+    y = __fmul_rn(q, s);
+  }
+};
+
+// K2  NQ:62-118.  Per element (q, y recomputed in registers instead of re-read from HBM):
+//   nz = (y == 0) ? eps : y                                   NQ:63
+//   r  = |dy| / |nz|                                          NQ:64
+//   max|q|                                                    NQ:68 / NQ:94
+//   below = !(r >= lambda)  (NaN counts as below, like tf.where on r >= lambda)   NQ:97,107
+//   sum  += -|tanh(lambda - r)| for below elements            NQ:109
+// acc.a = sum, acc.b = n_below, acc.c = max|q|.  The group-wide AND of NQ:97 is n_below == 0,
+// resolved in the second stage, which is what lets this be a single pass.
+template <bool EXT>
+struct BwdThresholdOp {
+  QMode qm;
+  float lam;
+  static constexpr bool kIn2 = true, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
+  __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
+  __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; x.b += y.b; x.c = fmaxf(x.c, y.c); }
+  __device__ __forceinline__ void elem(float p, float dy, float s, const float4&, const Job&, Acc& acc, float& dx, float&) const {
+    const float q = quant_code<EXT>(p, s, qm);
+    const float y = __fmul_rn(q, s);
+    const float nz = (y == 0.0f) ? kEps : y;
+    const float r = __fdiv_rn(fabsf(dy), fabsf(nz));
+    acc.c = fmaxf(acc.c, fabsf(q));
+    if (!(r >= lam)) {
+      acc.b += 1u;
+      acc.a -= fabsf(tanhf(__fsub_rn(lam, r)));
+    }
+    dx = dy;   // NQ:118: dP is dy itself
+  }
+};
+
+// ------------------------------------------------------------------ K4 second stage
+// One block per group.  Walks the group's partials in index order with a fixed
+// thread->partial assignment, then a fixed shuffle/shared-memory tree: deterministic.
+enum { FIN_THRESHOLD = 0 };
+
+__device__ __forceinline__ void finalize_group(const FinJob& f, long long g) {
+  const long long K = (f.regime == REG_ROW) ? f.outer * f.nseg : f.nchunks * f.inner;
+  double sum = 0.0;
+  unsigned long long cnt = 0ull;
+  float mx = 0.f;
+  for (long long k = threadIdx.x; k < K; k += kFinThreads) {
+    const float4 v = f.part[partial_index(f, g, k)];
+    sum += (double)v.x;
+    cnt += (unsigned long long)__float_as_uint(v.y);
+    mx = fmaxf(mx, v.z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double ssum[kFinThreads / 32];
+  __shared__ unsigned long long scnt[kFinThreads / 32];
+  __shared__ float smx[kFinThreads / 32];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; scnt[w] = cnt; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = ssum[0]; cnt = scnt[0]; mx = smx[0];
+#pragma unroll
+    for (int i = 1; i < kFinThreads / 32; ++i) { sum += ssum[i]; cnt += scnt[i]; mx = fmaxf(mx, smx[i]); }
+    // NQ:103-116: all above -> every element contributes c0 = -|tanh(lambda)| (mean = c0),
+    // otherwise the mean of the below-threshold terms over ALL N_g elements; times max|q|.
+    const double n_g = (double)f.outer * (double)f.inner;
+    const float mean = (cnt == 0ull) ? f.p1 : (float)(sum / n_g);
+    f.ds[g] = __fmul_rn(mean, mx);
+  }
+}
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinJob f) {
+  finalize_group(f, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kFinThreads) mt_finalize_kernel(const __grid_constant__ FinTable tab) {
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].group_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const FinJob& f = tab.job[lo];
+  finalize_group(f, blockIdx.x - f.group_begin);
+}
+
+// ------------------------------------------------------------------ host side
+Job make_job(const Geom& g, const float* P, const float* s, const float* dy, float* y, float* dX,
+             void* codes, int codes_dtype, float4* part) {
+  Job j{};
+  j.P = P; j.s = s; j.dy = dy; j.y = y; j.dX = dX; j.codes = codes; j.part = part;
+  j.outer = g.outer; j.C = g.C; j.inner = g.inner; j.W = g.W; j.units = g.units;
+  j.nchunks = g.nchunks; j.ncol = g.ncol;
+  j.regime = g.regime; j.vec = g.vec_ok; j.seg = g.seg; j.nseg = g.nseg;
+  j.bx = g.bx; j.by = g.by; j.rpc = g.rpc; j.codes_dtype = codes_dtype;
+  j.stream_hint = (g.n * 4 > kStreamBytes) ? 1 : 0;
+  j.write_dx = (dX != nullptr && dX != dy) ? 1 : 0;
+  j.block_begin = 0; j.nblocks = (unsigned)g.nblocks;
+  return j;
+}
+
+static FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, float lam) {
+  FinJob f{};
+  f.part = part; f.ds = ds; f.s = s;
+  f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
+  f.regime = g.regime; f.mode = FIN_THRESHOLD;
+  f.p0 = lam;
+  f.p1 = -fabsf(tanhf(lam));   // c0 of NQ:79 / NQ:105
+  return f;
+}
+
+// Internal launch helpers shared with lq_host.cu.
+int fq_fwd_launch(const Geom& g, const float* P, const float* s, float* y, void* codes, int codes_dtype,
+                  const QMode& qm, cudaStream_t st) {
+  Job j = make_job(g, P, s, nullptr, y, nullptr, codes, codes_dtype, nullptr);
+  if (qm.ext) { FwdOp<true> op{qm}; return launch_job(j, op, st); }
+  FwdOp<false> op{qm};
+  return launch_job(j, op, st);
+}
+
+int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const float* s, float lam,
+                           float* dX, float4* part, const QMode& qm, cudaStream_t st) {
+  Job j = make_job(g, P, s, dy, nullptr, dX, nullptr, 0, part);
+  if (qm.ext) { BwdThresholdOp<true> op{qm, lam}; return launch_job(j, op, st); }
+  BwdThresholdOp<false> op{qm, lam};
+  return launch_job(j, op, st);
+}
+
+int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st) {
+  FinJob f = make_fin(g, part, ds, s, lam);
+  finalize_kernel<<<dim3((unsigned)g.C), dim3(kFinThreads), 0, st>>>(f);
+  return cuda_fail(cudaGetLastError(), "finalize launch");
+}
+
+int check_blocks(const Geom& g) {
+  if (g.nblocks > 0x7fffffffll) { set_error("tensor too large for one grid (%lld blocks)", g.nblocks); return LQ_E_BADSHAPE; }
+  return LQ_OK;
+}
+
+}  // namespace lq
+
+using namespace lq;
+
+extern "C" int lq_fq_fwd(const float* P, const float* s, float* y, void* codes, int codes_dtype,
+                         int64_t outer, int64_t C, int64_t inner, int round_mode, float qmin, float qmax,
+                         lq_stream_t stream) {
+  int rc = check_dims(outer, C, inner);
+  if (rc) return rc;
+  if (outer * C * inner == 0) return LQ_OK;
+  if (!P || !s || !y) { set_error("lq_fq_fwd: null P/s/y"); return LQ_E_NULLPTR; }
+  if (codes_dtype < LQ_CODES_NONE || codes_dtype > LQ_CODES_I8 || (codes && codes_dtype == LQ_CODES_NONE)) {
+    set_error("lq_fq_fwd: bad codes_dtype %d", codes_dtype); return LQ_E_BADMODE;
+  }
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  const bool al = aligned16(P) && aligned16(y) && (!codes || codes_dtype == LQ_CODES_I8 || aligned16(codes));
+  Geom g = make_geom(outer, C, inner, al);
+  if ((rc = check_blocks(g))) return rc;
+  return fq_fwd_launch(g, P, s, y, codes_dtype == LQ_CODES_NONE ? nullptr : codes, codes_dtype, qm, (cudaStream_t)stream);
+}
+
+extern "C" int lq_fq_bwd_threshold(const float* dy, const float* P, const float* s, float penalty_threshold,
+                                   float* dX, float* ds, int64_t outer, int64_t C, int64_t inner,
+                                   int round_mode, float qmin, float qmax,
+                                   void* ws, size_t ws_bytes, lq_stream_t stream) {
+  int rc = check_dims(outer, C, inner);
+  if (rc) return rc;
+  if (!dy || !P || !s || !ds) { set_error("lq_fq_bwd_threshold: null dy/P/s/ds"); return LQ_E_NULLPTR; }
+  if (outer * C * inner == 0) return LQ_OK;
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  const bool wr = (dX != nullptr && dX != dy);
+  const bool al = aligned16(P) && aligned16(dy) && (!wr || aligned16(dX));
+  Geom g = make_geom(outer, C, inner, al);
+  if ((rc = check_blocks(g))) return rc;
+  const size_t need = align256((size_t)g.npartials * sizeof(float4));
+  if (!ws || ws_bytes < need || !aligned16(ws)) {
+    set_error("lq_fq_bwd_threshold: workspace %zu B (16-B aligned) needed, got %zu", need, ws_bytes);
+    return LQ_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = fq_bwd_elements_launch(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
+  return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), ds, s, penalty_threshold, st);
+}
+
+extern "C" int lq_fq_bwd_ste(const float* dy, float* dX, float* ds, int64_t n_elems, int64_t C,
+                             lq_stream_t stream) {
+  if (n_elems < 0 || C < 0) { set_error("lq_fq_bwd_ste: negative size"); return LQ_E_BADSHAPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dX && dX != dy && n_elems > 0) {
+    if (!dy) { set_error("lq_fq_bwd_ste: null dy"); return LQ_E_NULLPTR; }
+    int rc = cuda_fail(cudaMemcpyAsync(dX, dy, (size_t)n_elems * 4, cudaMemcpyDeviceToDevice, st), "dX = dy");
+    if (rc) return rc;
+  }
+  if (ds && C > 0) return cuda_fail(cudaMemsetAsync(ds, 0, (size_t)C * 4, st), "ds = 0");   // CL:62
+  return LQ_OK;
+}
+
+// ------------------------------------------------------------------ multi-tensor forms
+extern "C" int lq_mt_fq_fwd(const lq_tensor_desc* descs, int n, int round_mode, float qmin, float qmax,
+                            lq_stream_t stream) {
+  if (n < 0) { set_error("lq_mt_fq_fwd: n < 0"); return LQ_E_BADSHAPE; }
+  if (n && !descs) { set_error("lq_mt_fq_fwd: null descs"); return LQ_E_NULLPTR; }
+  int rc = 0;
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i0 = 0; i0 < n; i0 += kMaxMT) {
+    JobTable tab{};
+    for (int i = i0; i < n && i < i0 + kMaxMT; ++i) {
+      const lq_tensor_desc& d = descs[i];
+      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
+      if (d.outer * d.C * d.inner == 0) continue;
+      if (!d.P || !d.s || !d.y) { set_error("lq_mt_fq_fwd: desc %d has null P/s/y", i); return LQ_E_NULLPTR; }
+      Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.y));
+      if ((rc = check_blocks(g))) return rc;
+      tab.job[tab.n++] = make_job(g, d.P, d.s, nullptr, d.y, nullptr, nullptr, 0, nullptr);
+    }
+    if (qm.ext) { FwdOp<true> op{qm}; rc = launch_mt(tab, op, st); }
+    else { FwdOp<false> op{qm}; rc = launch_mt(tab, op, st); }
+    if (rc) return rc;
+  }
+  return LQ_OK;
+}
+
+extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_threshold, int scale_grad_mode,
+                            int round_mode, float qmin, float qmax,
+                            void* ws, size_t ws_bytes, lq_stream_t stream) {
+  if (n < 0) { set_error("lq_mt_fq_bwd: n < 0"); return LQ_E_BADSHAPE; }
+  if (n && !descs) { set_error("lq_mt_fq_bwd: null descs"); return LQ_E_NULLPTR; }
+  if (scale_grad_mode != LQ_SGRAD_NONE && scale_grad_mode != LQ_SGRAD_THRESHOLD) {
+    set_error("lq_mt_fq_bwd: bad scale_grad_mode %d", scale_grad_mode); return LQ_E_BADMODE;
+  }
+  int rc = 0;
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (scale_grad_mode == LQ_SGRAD_NONE) {     // CL:61-62 / PI:62-64 for every tensor
+    for (int i = 0; i < n; ++i) {
+      const lq_tensor_desc& d = descs[i];
+      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
+      if ((rc = lq_fq_bwd_ste(d.dy, d.dX, d.ds, d.outer * d.C * d.inner, d.C, stream))) return rc;
+    }
+    return LQ_OK;
+  }
+  size_t off = 0;
+  for (int i0 = 0; i0 < n; i0 += kMaxMT) {
+    JobTable tab{};
+    FinTable fin{};
+    unsigned groups = 0;
+    for (int i = i0; i < n && i < i0 + kMaxMT; ++i) {
+      const lq_tensor_desc& d = descs[i];
+      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
+      if (d.outer * d.C * d.inner == 0) continue;
+      if (!d.P || !d.s || !d.dy || !d.ds) { set_error("lq_mt_fq_bwd: desc %d has null P/s/dy/ds", i); return LQ_E_NULLPTR; }
+      const bool wr = (d.dX != nullptr && d.dX != d.dy);
+      Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dy) && (!wr || aligned16(d.dX)));
+      if ((rc = check_blocks(g))) return rc;
+      const size_t need = align256((size_t)g.npartials * sizeof(float4));
+      if (!ws || off + need > ws_bytes) {
+        set_error("lq_mt_fq_bwd: workspace too small (need > %zu B, got %zu)", off + need, ws_bytes);
+        return LQ_E_WORKSPACE;
+      }
+      float4* part = reinterpret_cast<float4*>(static_cast<char*>(ws) + off);
+      off += need;
+      tab.job[tab.n++] = make_job(g, d.P, d.s, d.dy, nullptr, d.dX, nullptr, 0, part);
+      FinJob f = make_fin(g, part, d.ds, d.s, penalty_threshold);
+      f.group_begin = groups;
+      groups += (unsigned)d.C;
+      fin.job[fin.n++] = f;
+    }
+    if (tab.n == 0) continue;
+    if (qm.ext) { BwdThresholdOp<true> op{qm, penalty_threshold}; rc = launch_mt(tab, op, st); }
+    else { BwdThresholdOp<false> op{qm, penalty_threshold}; rc = launch_mt(tab, op, st); }
+    if (rc) return rc;
+    mt_finalize_kernel<<<dim3(groups), dim3(kFinThreads), 0, st>>>(fin);
+    if ((rc = cuda_fail(cudaGetLastError(), "mt finalize launch"))) return rc;
+  }
+  return LQ_OK;
+}

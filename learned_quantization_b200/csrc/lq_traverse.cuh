@@ -1,0 +1,311 @@
+// lq_traverse.cuh -- the two traversals (ROW / COL, see lq_common.cuh) as templates over an
+// element operator.  An operator provides
+//   struct Acc { float a; unsigned b; float c; }  semantics via  init / combine
+//   static constexpr bool kIn2      second input array (Job::dy) is read
+//   static constexpr bool kOutIsY   out0 goes to Job::y (else to Job::dX when Job::write_dx)
+//   static constexpr bool kCodes    out1 is the integer code, written to Job::codes if set
+//   static constexpr bool kReduce   per-unit partials are produced
+//   static constexpr bool kAux      per-group float4 Job::gaux[g] is fetched next to the scale
+//   elem(p, in2, s, aux, job, acc, out0, out1)
+#pragma once
+#include "lq_common.cuh"
+
+namespace lq {
+
+struct Acc {
+  float a; unsigned b; float c;
+};
+
+__device__ __forceinline__ float4 pack_acc(const Acc& x) {
+  return make_float4(x.a, __uint_as_float(x.b), x.c, 0.0f);
+}
+__device__ __forceinline__ Acc unpack_acc(const float4& v) {
+  Acc x; x.a = v.x; x.b = __float_as_uint(v.y); x.c = v.z; return x;
+}
+
+template <class Op>
+__device__ __forceinline__ Acc warp_reduce_acc(Acc x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Acc y;
+    y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
+    y.b = __shfl_xor_sync(0xffffffffu, x.b, o);
+    y.c = __shfl_xor_sync(0xffffffffu, x.c, o);
+    Op::combine(x, y);
+  }
+  return x;
+}
+
+__device__ __forceinline__ void store_code(void* codes, int dtype, long long idx, float q) {
+  if (dtype == LQ_CODES_F32) reinterpret_cast<float*>(codes)[idx] = q;
+  else if (dtype == LQ_CODES_I32) reinterpret_cast<int*>(codes)[idx] = (int)q;
+  else reinterpret_cast<signed char*>(codes)[idx] = (signed char)(int)q;  // wraps like .astype(int8)
+}
+
+// ------------------------------------------------------------------------- ROW regime
+template <class Op, bool STREAM, bool VEC>
+__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op) {
+  const int lane = threadIdx.x & 31;
+  const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
+  if (unit >= j.units) return;
+  const long long row = unit / j.nseg;
+  const int sg = (int)(unit - row * j.nseg);
+  const long long grp = row % j.C;
+  const float s = __ldg(j.s + grp);
+  const float4 aux = Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long base = row * j.inner + (long long)sg * j.seg;
+  const long long rem = j.inner - (long long)sg * j.seg;
+  const int len = rem < j.seg ? (int)rem : j.seg;
+
+  Acc acc; Op::init(acc);
+  float* out = Op::kOutIsY ? j.y : j.dX;
+  const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
+
+  if constexpr (VEC) {
+    const int nvec = len >> 2;
+    const float4* P4 = reinterpret_cast<const float4*>(j.P + base);
+    const float4* D4 = reinterpret_cast<const float4*>(j.dy + base);
+    float4* O4 = reinterpret_cast<float4*>(out + base);
+    for (int v0 = 0; v0 < nvec; v0 += 128) {
+      float4 p[4], d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 32 + lane;
+        if (v < nvec) {
+          p[u] = ld4<STREAM>(P4 + v);
+          if (Op::kIn2) d[u] = ld4<STREAM>(D4 + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * 32 + lane;
+        if (v < nvec) {
+          float4 o, c;
+          op.elem(p[u].x, Op::kIn2 ? d[u].x : 0.f, s, aux, j, acc, o.x, c.x);
+          op.elem(p[u].y, Op::kIn2 ? d[u].y : 0.f, s, aux, j, acc, o.y, c.y);
+          op.elem(p[u].z, Op::kIn2 ? d[u].z : 0.f, s, aux, j, acc, o.z, c.z);
+          op.elem(p[u].w, Op::kIn2 ? d[u].w : 0.f, s, aux, j, acc, o.w, c.w);
+          if (wr) st4<STREAM>(O4 + v, o);
+          if (Op::kCodes && j.codes) {
+            const long long e = base + 4ll * v;
+            store_code(j.codes, j.codes_dtype, e + 0, c.x);
+            store_code(j.codes, j.codes_dtype, e + 1, c.y);
+            store_code(j.codes, j.codes_dtype, e + 2, c.z);
+            store_code(j.codes, j.codes_dtype, e + 3, c.w);
+          }
+        }
+      }
+    }
+  } else {
+    for (int e0 = 0; e0 < len; e0 += 128) {
+      float p[4], d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 32 + lane;
+        if (e < len) {
+          p[u] = ld1<STREAM>(j.P + base + e);
+          if (Op::kIn2) d[u] = ld1<STREAM>(j.dy + base + e);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * 32 + lane;
+        if (e < len) {
+          float o, c;
+          op.elem(p[u], Op::kIn2 ? d[u] : 0.f, s, aux, j, acc, o, c);
+          if (wr) st1<STREAM>(out + base + e, o);
+          if (Op::kCodes && j.codes) store_code(j.codes, j.codes_dtype, base + e, c);
+        }
+      }
+    }
+  }
+  if (Op::kReduce) {
+    acc = warp_reduce_acc<Op>(acc);
+    if (lane == 0) j.part[unit] = pack_acc(acc);
+  }
+}
+
+// ------------------------------------------------------------------------- COL regime
+template <class Op, bool STREAM, bool VEC>
+__device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op, Acc* smem) {
+  constexpr int V = VEC ? 4 : 1;
+  const long long chunk = blk % j.nchunks;
+  const long long cb = blk / j.nchunks;
+  const int t = threadIdx.x;
+  const int ty = t / j.bx;
+  const int tx = t - ty * j.bx;
+  const long long cv = cb * j.bx + tx;
+  const bool active = (ty < j.by) && (cv < j.ncol);
+  const long long col0 = cv * V;
+  const long long r0 = chunk * j.rpc;
+  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+
+  float s[V];
+  float4 aux[V];
+  Acc acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    Op::init(acc[k]);
+    const long long grp = active ? (col0 + k) / j.inner : 0;
+    s[k] = active ? __ldg(j.s + grp) : 1.0f;
+    aux[k] = (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float* out = Op::kOutIsY ? j.y : j.dX;
+  const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
+
+  if (active) {
+    const long long step = j.by;
+    for (long long r = r0 + ty; r < r1; r += 4 * step) {
+      float p[4][V], d[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * step;
+        if (rr < r1) {
+          const long long e = rr * j.W + col0;
+          if constexpr (VEC) {
+            const float4 pv = ld4<STREAM>(reinterpret_cast<const float4*>(j.P + e));
+            p[u][0] = pv.x; p[u][1] = pv.y; p[u][2] = pv.z; p[u][3] = pv.w;
+            if (Op::kIn2) {
+              const float4 dv = ld4<STREAM>(reinterpret_cast<const float4*>(j.dy + e));
+              d[u][0] = dv.x; d[u][1] = dv.y; d[u][2] = dv.z; d[u][3] = dv.w;
+            }
+          } else {
+            p[u][0] = ld1<STREAM>(j.P + e);
+            if (Op::kIn2) d[u][0] = ld1<STREAM>(j.dy + e);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * step;
+        if (rr < r1) {
+          const long long e = rr * j.W + col0;
+          float o[V], c[V];
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            op.elem(p[u][k], Op::kIn2 ? d[u][k] : 0.f, s[k], aux[k], j, acc[k], o[k], c[k]);
+          if (wr) {
+            if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(out + e), make_float4(o[0], o[1], o[2], o[3]));
+            else st1<STREAM>(out + e, o[0]);
+          }
+          if (Op::kCodes && j.codes) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+          }
+        }
+      }
+    }
+  }
+
+  if (Op::kReduce) {
+    // fixed-shape tree over the threads that share a column (same tx, ty = 0..by-1)
+    if (j.by > 1) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) smem[k * kThreads + t] = acc[k];
+      int span = 1;
+      while (span < j.by) span <<= 1;
+      for (int stride = span >> 1; stride >= 1; stride >>= 1) {
+        __syncthreads();
+        if (ty < stride && ty + stride < j.by && ty < j.by) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            Acc mine = smem[k * kThreads + t];
+            Op::combine(mine, smem[k * kThreads + t + stride * j.bx]);
+            smem[k * kThreads + t] = mine;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = smem[k * kThreads + t];
+    }
+    if (ty == 0 && cv < j.ncol) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) j.part[chunk * j.W + col0 + k] = pack_acc(acc[k]);
+    }
+  }
+}
+
+template <class Op, bool STREAM, bool VEC>
+__device__ __forceinline__ void run_job(const Job& j, unsigned blk, const Op& op, Acc* smem) {
+  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op);
+  else run_col<Op, STREAM, VEC>(j, blk, op, smem);
+}
+
+// Single-tensor kernels: the Job travels in the kernel parameters.  One instantiation per
+// regime so that each keeps only its own registers (the ROW kernel is the bandwidth path).
+template <class Op, bool STREAM, bool VEC>
+__global__ void __launch_bounds__(kThreads) row_kernel(const __grid_constant__ Job j, const Op op) {
+  run_row<Op, STREAM, VEC>(j, blockIdx.x, op);
+}
+template <class Op, bool STREAM, bool VEC>
+__global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ Job j, const Op op) {
+  __shared__ Acc smem[Op::kReduce ? 4 * kThreads : 1];
+  run_col<Op, STREAM, VEC>(j, blockIdx.x, op, smem);
+}
+
+// Multi-tensor kernel: block -> tensor by binary search over block_begin.
+template <class Op>
+__global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
+  __shared__ Acc smem[Op::kReduce ? 4 * kThreads : 1];
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const Job& j = tab.job[lo];
+  const unsigned blk = blockIdx.x - j.block_begin;
+  if (j.vec) run_job<Op, false, true>(j, blk, op, smem);
+  else run_job<Op, false, false>(j, blk, op, smem);
+}
+
+constexpr int kFinThreads = 128;
+
+__device__ __forceinline__ long long partial_index(const FinJob& f, long long g, long long k) {
+  if (f.regime == REG_ROW) {
+    const long long o = k / f.nseg, sg = k - o * f.nseg;
+    return (o * f.C + g) * f.nseg + sg;
+  }
+  const long long ch = k / f.inner, ci = k - ch * f.inner;
+  return ch * f.W + g * f.inner + ci;
+}
+
+// ---- host side
+int fq_fwd_launch(const Geom& g, const float* P, const float* s, float* y, void* codes, int codes_dtype,
+                  const QMode& qm, cudaStream_t st);
+int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const float* s, float lam,
+                           float* dX, float4* part, const QMode& qm, cudaStream_t st);
+int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st);
+int check_blocks(const Geom& g);
+Job make_job(const Geom& g, const float* P, const float* s, const float* dy, float* y, float* dX,
+             void* codes, int codes_dtype, float4* part);
+
+template <class Op>
+int launch_job(const Job& j, const Op& op, cudaStream_t st) {
+  if (j.nblocks == 0) return LQ_OK;
+  dim3 grid(j.nblocks), block(kThreads);
+#define LQ_LAUNCH(KERNEL)                                                            \
+  do {                                                                               \
+    if (j.stream_hint) {                                                             \
+      if (j.vec) KERNEL<Op, true, true><<<grid, block, 0, st>>>(j, op);              \
+      else KERNEL<Op, true, false><<<grid, block, 0, st>>>(j, op);                   \
+    } else {                                                                         \
+      if (j.vec) KERNEL<Op, false, true><<<grid, block, 0, st>>>(j, op);             \
+      else KERNEL<Op, false, false><<<grid, block, 0, st>>>(j, op);                  \
+    }                                                                                \
+  } while (0)
+  if (j.regime == REG_ROW) LQ_LAUNCH(row_kernel); else LQ_LAUNCH(col_kernel);
+#undef LQ_LAUNCH
+  return cuda_fail(cudaGetLastError(), "kernel launch");
+}
+
+template <class Op>
+int launch_mt(JobTable& tab, const Op& op, cudaStream_t st) {
+  unsigned total = 0;
+  for (int i = 0; i < tab.n; ++i) { tab.job[i].block_begin = total; total += tab.job[i].nblocks; }
+  if (total == 0) return LQ_OK;
+  mt_kernel<Op><<<dim3(total), dim3(kThreads), 0, st>>>(tab, op);
+  return cuda_fail(cudaGetLastError(), "multi-tensor kernel launch");
+}
+
+}  // namespace lq

@@ -1,0 +1,250 @@
+"""Thin torch-side wrappers over the C-ABI: raw device pointers + the current stream.
+
+torch is used for device memory, streams and autograd plumbing only; all arithmetic of
+the hot path happens inside liblq.so.  Nothing here falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import TensorDesc, check, lib
+
+EPS_FLOAT32 = 1.1920928955078125e-07           # np.finfo(np.float32).eps (NQ:11)
+SCALE_INIT = 1.1920928955078125e-05            # eps_float32 * 100 in fp32 (NQ:156-158)
+NEG_INF, POS_INF = -math.inf, math.inf
+
+
+# --------------------------------------------------------------------- host logic
+def scale_shape(param_shape: Sequence[int], orientation: str) -> Tuple[int, ...]:
+    """Scale shape per orientation, CustomQuantizedScaleLayer.build (NQ:147-197)."""
+    n = len(param_shape)
+    if orientation == "rowwise":
+        return tuple(int(param_shape[i]) if i == 0 else 1 for i in range(n))
+    if orientation == "columnwise":
+        return tuple(int(param_shape[i]) if i == 1 else 1 for i in range(n))
+    if orientation == "channelwise":
+        return tuple(int(param_shape[i]) if i == 2 else 1 for i in range(n))
+    if orientation == "scalar":
+        return (1,)
+    raise ValueError(
+        f"Invalid scaler application: {orientation}. Expected rowwise, columnwise or scalar.")
+
+
+def group_layout(param_shape: Sequence[int], s_shape: Sequence[int]) -> Tuple[int, int, int]:
+    """[outer, C, inner] view with group(idx) = (idx // inner) % C for a broadcastable scale."""
+    param_shape = tuple(int(d) for d in param_shape)
+    s_shape = tuple(int(d) for d in s_shape)
+    total = 1
+    for d in param_shape:
+        total *= d
+    if len(s_shape) == 1 and len(param_shape) != 1:
+        if s_shape[0] != 1:
+            raise ValueError(f"scale shape {s_shape} does not broadcast over parameter shape {param_shape}")
+        return 1, 1, total
+    if len(s_shape) != len(param_shape):
+        raise ValueError(f"scale shape {s_shape} does not broadcast over parameter shape {param_shape}")
+    axes = [i for i, d in enumerate(s_shape) if d != 1]
+    if len(axes) > 1:
+        raise ValueError(f"scale shape {s_shape}: at most one non-1 axis is supported")
+    if not axes:
+        return 1, 1, total
+    ax = axes[0]
+    if s_shape[ax] != param_shape[ax]:
+        raise ValueError(f"scale shape {s_shape} does not broadcast over parameter shape {param_shape}")
+    outer = 1
+    for d in param_shape[:ax]:
+        outer *= d
+    inner = 1
+    for d in param_shape[ax + 1:]:
+        inner *= d
+    return outer, param_shape[ax], inner
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("learned_quantization_b200 runs on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+        if t.dtype != torch.float32:
+            raise TypeError(f"fp32 tensors only, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("tensors must be contiguous")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# One growable workspace per (device, stream): kernels on one stream are ordered, so
+# consecutive calls may reuse it.
+_WS: dict = {}
+
+
+def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
+    key = (device.index, _stream(), tag)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def make_desc(P=None, s=None, y=None, dy=None, dX=None, ds=None, layout=(0, 0, 0), flags=0) -> TensorDesc:
+    ptr = lambda t: None if t is None else t.data_ptr()
+    return TensorDesc(P=ptr(P), s=ptr(s), y=ptr(y), dy=ptr(dy), dX=ptr(dX), ds=ptr(ds),
+                      outer=layout[0], C=layout[1], inner=layout[2], flags=flags, reserved=0)
+
+
+def desc_array(descs: Sequence[TensorDesc]):
+    return (TensorDesc * len(descs))(*descs)
+
+
+def workspace_bytes(descs, phase: int) -> int:
+    out = C.c_size_t()
+    arr = descs if not isinstance(descs, (list, tuple)) else desc_array(descs)
+    check(lib.lq_workspace_bytes(arr, len(arr), phase, C.byref(out)))
+    return out.value
+
+
+# --------------------------------------------------------------------- operators
+def fq_fwd(P: torch.Tensor, s: torch.Tensor, layout=None, *, codes_dtype: Optional[torch.dtype] = None,
+           round_mode: int = _lib.LQ_ROUND_FLOOR, qmin: float = NEG_INF, qmax: float = POS_INF,
+           out: Optional[torch.Tensor] = None):
+    """y = floor(P / s) * s (NQ:55-60).  Returns y, or (y, codes) when codes_dtype is given."""
+    _require_cuda(P, s)
+    layout = layout or group_layout(P.shape, s.shape)
+    y = torch.empty_like(P) if out is None else out
+    codes, cd = None, _lib.LQ_CODES_NONE
+    if codes_dtype is not None:
+        cd = {torch.float32: _lib.LQ_CODES_F32, torch.int32: _lib.LQ_CODES_I32, torch.int8: _lib.LQ_CODES_I8}[codes_dtype]
+        codes = torch.empty(P.shape, dtype=codes_dtype, device=P.device)
+    with torch.cuda.device(P.device):
+        check(lib.lq_fq_fwd(P.data_ptr(), s.data_ptr(), y.data_ptr(),
+                            None if codes is None else codes.data_ptr(), cd,
+                            layout[0], layout[1], layout[2], round_mode, qmin, qmax, _stream()))
+    return y if codes is None else (y, codes)
+
+
+def fq_bwd_threshold(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, penalty_threshold: float,
+                     layout=None, *, write_dx: bool = False,
+                     round_mode: int = _lib.LQ_ROUND_FLOOR, qmin: float = NEG_INF, qmax: float = POS_INF):
+    """(dX, ds) of NQ:62-118.  dX is dy itself unless write_dx asks for a separate copy."""
+    _require_cuda(dy, P, s)
+    layout = layout or group_layout(P.shape, s.shape)
+    ds = torch.empty_like(s)
+    dX = torch.empty_like(dy) if write_dx else None
+    d = make_desc(layout=layout)
+    need = workspace_bytes([d], _lib.LQ_PHASE_BWD)
+    ws = workspace(need, P.device)
+    with torch.cuda.device(P.device):
+        check(lib.lq_fq_bwd_threshold(dy.data_ptr(), P.data_ptr(), s.data_ptr(), float(penalty_threshold),
+                                      None if dX is None else dX.data_ptr(), ds.data_ptr(),
+                                      layout[0], layout[1], layout[2], round_mode, qmin, qmax,
+                                      ws.data_ptr(), ws.numel(), _stream()))
+    return (dy if dX is None else dX), ds
+
+
+def fq_bwd_ste(dy: torch.Tensor, s: torch.Tensor):
+    """(dX, ds) of CL:61-62 / PI:62-64: dX is dy, ds is zeros."""
+    _require_cuda(dy, s)
+    ds = torch.empty_like(s)
+    with torch.cuda.device(dy.device):
+        check(lib.lq_fq_bwd_ste(dy.data_ptr(), None, ds.data_ptr(), dy.numel(), s.numel(), _stream()))
+    return dy, ds
+
+
+def scale_constraint_(s: torch.Tensor, min_value: float = SCALE_INIT) -> torch.Tensor:
+    """In-place MinValueConstraint (NQ:35-46)."""
+    _require_cuda(s)
+    with torch.cuda.device(s.device):
+        check(lib.lq_scale_constraint(s.data_ptr(), s.numel(), float(min_value), _stream()))
+    return s
+
+
+# --------------------------------------------------------------------- multi-tensor
+def mt_fq_fwd(Ps: Sequence[torch.Tensor], ss: Sequence[torch.Tensor], ys: Sequence[torch.Tensor],
+              layouts=None, round_mode=_lib.LQ_ROUND_FLOOR, qmin=NEG_INF, qmax=POS_INF) -> None:
+    _require_cuda(*Ps, *ss, *ys)
+    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    arr = desc_array([make_desc(P=p, s=s, y=y, layout=l) for p, s, y, l in zip(Ps, ss, ys, layouts)])
+    with torch.cuda.device(Ps[0].device):
+        check(lib.lq_mt_fq_fwd(arr, len(arr), round_mode, qmin, qmax, _stream()))
+
+
+def mt_fq_bwd(dys, Ps, ss, dss, penalty_threshold: float, layouts=None, dXs=None,
+              scale_grad_mode=_lib.LQ_SGRAD_THRESHOLD, round_mode=_lib.LQ_ROUND_FLOOR,
+              qmin=NEG_INF, qmax=POS_INF) -> None:
+    _require_cuda(*dys, *Ps, *ss, *dss)
+    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    dXs = dXs or [None] * len(Ps)
+    arr = desc_array([make_desc(P=p, s=s, dy=dy, dX=dx, ds=ds, layout=l)
+                      for p, s, dy, dx, ds, l in zip(Ps, ss, dys, dXs, dss, layouts)])
+    need = workspace_bytes(arr, _lib.LQ_PHASE_BWD)
+    ws = workspace(need, Ps[0].device)
+    with torch.cuda.device(Ps[0].device):
+        check(lib.lq_mt_fq_bwd(arr, len(arr), float(penalty_threshold), scale_grad_mode, round_mode, qmin, qmax,
+                               ws.data_ptr(), ws.numel(), _stream()))
+
+
+# --------------------------------------------------------------------- penalties
+def penalty_fwd(kind: int, Ps, ss, layouts=None):
+    """compute_*_penalty() over tensors (LF:75-116 / 161-195 / 240-275). Returns (scalar, ws)."""
+    _require_cuda(*Ps, *ss)
+    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    arr = desc_array([make_desc(P=p, s=s, layout=l) for p, s, l in zip(Ps, ss, layouts)])
+    need = workspace_bytes(arr, _lib.LQ_PHASE_PENALTY_FWD)
+    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=Ps[0].device)   # kept for the backward
+    out = torch.empty((), dtype=torch.float32, device=Ps[0].device)
+    with torch.cuda.device(Ps[0].device):
+        check(lib.lq_penalty_fwd(kind, arr, len(arr), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out, ws
+
+
+def penalty_bwd(kind: int, Ps, ss, ws: torch.Tensor, upstream: float = 1.0,
+                upstream_dev: Optional[torch.Tensor] = None, layouts=None, dXs=None, dss=None,
+                accumulate: bool = False):
+    """Gradients of upstream*penalty w.r.t. every P and s. Returns (dXs, dss)."""
+    _require_cuda(*Ps, *ss)
+    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    need_dx = kind != _lib.LQ_PEN_INVERSE
+    if dXs is None:
+        dXs = [torch.empty_like(p) if need_dx else None for p in Ps]
+    if dss is None:
+        dss = [torch.empty_like(s) for s in ss]
+    flags = (_lib.LQ_F_ACCUM_DX | _lib.LQ_F_ACCUM_DS) if accumulate else 0
+    arr = desc_array([make_desc(P=p, s=s, dX=dx, ds=ds, layout=l, flags=flags)
+                      for p, s, dx, ds, l in zip(Ps, ss, dXs, dss, layouts)])
+    with torch.cuda.device(Ps[0].device):
+        check(lib.lq_penalty_bwd(kind, arr, len(arr), float(upstream),
+                                 None if upstream_dev is None else upstream_dev.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _stream()))
+    return dXs, dss
+
+
+# --------------------------------------------------------------------- host-buffer path
+def host_workspace_bytes(layout) -> int:
+    out = C.c_size_t()
+    check(lib.lq_host_workspace_bytes(layout[0], layout[1], layout[2], C.byref(out)))
+    return out.value
+
+
+def host_fq_fwd_bwd(hP: torch.Tensor, hs: torch.Tensor, hdy: torch.Tensor, penalty_threshold: float,
+                    hy: torch.Tensor, hds: torch.Tensor, layout, dev_ws: torch.Tensor,
+                    hdX: Optional[torch.Tensor] = None) -> None:
+    """Forward + threshold backward on HOST tensors (pinned recommended); synchronous."""
+    for t in (hP, hs, hdy, hy, hds):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("host_fq_fwd_bwd takes contiguous fp32 CPU tensors")
+    if not dev_ws.is_cuda:
+        raise RuntimeError("dev_ws must be a CUDA buffer (no CPU fallback)")
+    with torch.cuda.device(dev_ws.device):
+        check(lib.lq_host_fq_fwd_bwd(hP.data_ptr(), hs.data_ptr(), hdy.data_ptr(), float(penalty_threshold),
+                                     hy.data_ptr(), None if hdX is None else hdX.data_ptr(), hds.data_ptr(),
+                                     layout[0], layout[1], layout[2], dev_ws.data_ptr(), dev_ws.numel()))

@@ -1,0 +1,405 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI (ctypes), against the oracle
+and the committed reference-source fixtures.  Forward outputs and codes must be BIT-EXACT;
+scale gradients / loss terms within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, rel_err
+from oracle import lq_oracle as o
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def lq():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    import learned_quantization_b200 as pkg
+    return pkg
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def ds_close(got, ref, tol=TOL):
+    got = np.asarray(got, np.float64).reshape(-1)
+    ref = np.asarray(ref, np.float64).reshape(-1)
+    scale = max(float(np.max(np.abs(ref))), 1e-30) if ref.size else 1.0
+    # per-element relative error, with an absolute floor relative to the largest entry
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3 * scale)
+    err = np.where(np.isnan(got) & np.isnan(ref), 0.0, err)
+    return float(np.max(err)) <= tol if err.size else True
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_golden_forward_bit_exact_and_ds(lq, golden):
+    ops = lq.ops
+    n = 0
+    for c, P, s, dy, q_ref, y_ref, ds_ref in golden.op_cases():
+        Pd, sd, dyd = dev(P), dev(s), dev(dy)
+        y, codes = ops.fq_fwd(Pd, sd, codes_dtype=torch.float32)
+        assert bits_equal(host(y), y_ref), c
+        assert bits_equal(host(codes), q_ref), c
+        dX, ds = ops.fq_bwd_threshold(dyd, Pd, sd, c["lam"])
+        assert dX.data_ptr() == dyd.data_ptr()
+        assert ds_close(host(ds).reshape(ds_ref.shape), ds_ref), (c, host(ds), ds_ref)
+        dX2, ds2 = ops.fq_bwd_threshold(dyd, Pd, sd, c["lam"], write_dx=True)
+        assert bits_equal(host(dX2), dy) and bits_equal(host(ds2), host(ds)), c
+        n += 1
+    assert n >= 200
+
+
+def test_golden_autograd_modules(lq, golden):
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.custom_loss_terms.custom_components import custom_layers as cl
+    from learned_quantization_b200.paper_implementation.custom_components import custom_layers as pi
+    for c, P, s, dy, q_ref, y_ref, ds_ref in list(golden.op_cases())[::7]:
+        Pt, st = dev(P).requires_grad_(), dev(s).requires_grad_()
+        y = nq.my_custom_gradient(Pt, st, c["lam"])
+        y.backward(dev(dy))
+        assert bits_equal(host(y), y_ref) and bits_equal(host(Pt.grad), dy), c
+        assert st.grad.shape == st.shape and ds_close(host(st.grad), ds_ref), c
+    for c in golden.manifest["ste"]:
+        g = {k: golden[f"{c['id']}/{k}"] for k in ("P", "s", "dy", "q", "y", "ds")}
+        Pt, st = dev(g["P"]).requires_grad_(), dev(g["s"]).requires_grad_()
+        y = cl.my_custom_gradient(Pt, st) if c["module"].startswith("CL") else pi.my_custom_gradient(Pt, st, 1e-3)
+        y.backward(dev(g["dy"]))
+        assert bits_equal(host(y), g["y"]) and bits_equal(host(Pt.grad), g["dy"]), c
+        assert bits_equal(host(st.grad), g["ds"]) and not host(st.grad).any(), c
+
+
+def test_golden_scale_layer_shapes_and_errors(lq, golden):
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    for c in golden.manifest["shapes"]:
+        layer = nq.CustomQuantizedScaleLayer(penalty_threshold=0.0, initializer=None, orientation=c["orientation"])
+        layer.build(tuple(c["param"]), "cuda")
+        assert list(layer.scale.shape) == c["scale"], c
+        assert float(layer.scale.flatten()[0]) == 1.1920928955078125e-05
+    bad = nq.CustomQuantizedScaleLayer(penalty_threshold=0.0, initializer=None, orientation="diagonal")
+    with pytest.raises(ValueError) as e:
+        bad.build((3, 3), "cuda")
+    assert str(e.value) == golden.manifest["bad_orientation_raises"]
+    w = golden["constraint/in"]
+    out = nq.MinValueConstraint(golden.manifest["constraint"][0]["min_value"])(dev(w))
+    assert bits_equal(host(out), golden["constraint/out"])
+
+
+def test_golden_loss_terms(lq, golden):
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    kinds = {"compute_maxbin_penalty": _lib.LQ_PEN_MAXBIN, "compute_difference_penalty": _lib.LQ_PEN_DIFFERENCE,
+             "compute_inverse_penalty": _lib.LQ_PEN_INVERSE}
+    for c in golden.manifest["loss"]:
+        layers, grads = golden.loss_layers(c), golden.loss_grads(c)
+        Ps, ss, gP, gs = [], [], [], []
+        for (K, sK, b, sb), (gK, gsK, gb, gsb) in zip(layers, grads):
+            Ps += [dev(K), dev(b)]; ss += [dev(sK), dev(sb)]; gP += [gK, gb]; gs += [gsK, gsb]
+        kind = kinds[c["method"]]
+        out, ws = ops.penalty_fwd(kind, Ps, ss)
+        assert rel_err(host(out), golden[f"{c['id']}/penalty"]) < TOL, c
+        up = torch.tensor(1.0, device="cuda")
+        dXs, dss = ops.penalty_bwd(kind, Ps, ss, ws, 1.0, upstream_dev=up)
+        for i in range(len(Ps)):
+            if kind != _lib.LQ_PEN_INVERSE:
+                scale = max(float(np.max(np.abs(gP[i]))), 1e-30)
+                assert float(np.max(np.abs(host(dXs[i]).astype(np.float64) - gP[i]))) <= TOL * scale, (c, i)
+            scale = max(float(np.max(np.abs(gs[i]))), 1e-30)
+            assert float(np.max(np.abs(host(dss[i]).astype(np.float64).reshape(gs[i].shape) - gs[i]))) <= TOL * scale, (c, i)
+        # accumulate flag and host-scalar upstream: g <- 1 + 2.5 * grad
+        if kind != _lib.LQ_PEN_INVERSE:
+            acc_dX = [torch.ones_like(p) for p in Ps]
+            acc_ds = [torch.ones_like(s) for s in ss]
+            ops.penalty_bwd(kind, Ps, ss, ws, 2.5, dXs=acc_dX, dss=acc_ds, accumulate=True)
+            for i in range(len(Ps)):
+                scale = max(float(np.max(np.abs(gP[i]))), 1e-30)
+                assert float(np.max(np.abs(host(acc_dX[i]).astype(np.float64) - 1.0 - 2.5 * gP[i]))) <= 1e-6 + 3 * TOL * scale
+
+
+def test_golden_loss_classes_autograd(lq, golden, tmp_path):
+    import types
+    from learned_quantization_b200.custom_loss_terms.custom_components import custom_loss_functions as lf
+    for c in golden.manifest["loss"]:
+        if c.get("no_total"):
+            continue
+        mnist = c["module"] == "LF_MNIST"
+        layers, raw = [], []
+        for K, sK, b, sb in golden.loss_layers(c):
+            t = [dev(a).requires_grad_() for a in (K, sK, b, sb)]
+            ns = types.SimpleNamespace
+            if mnist:
+                layers.append(ns(W=t[0], nested_q_w_layer=ns(scale=t[1]), b=t[2], nested_q_b_layer=ns(scale=t[3])))
+            else:
+                layers.append(ns(kernel=t[0], nested_q_k_layer=ns(scale=t[1]), b=t[2], nested_q_b_layer=ns(scale=t[3])))
+            raw.append(t)
+        obj = getattr(lf, c["class"])(layers=layers, penalty_rate=c["gamma"], log_dir=str(tmp_path))
+        pen = getattr(obj, c["method"])()
+        assert rel_err(host(pen), golden[f"{c['id']}/penalty"]) < TOL
+        pen.backward()
+        for t, ref in zip(raw, golden.loss_grads(c)):
+            for tt, r in zip(t, ref):
+                got = np.zeros_like(r) if tt.grad is None else host(tt.grad)
+                assert float(np.max(np.abs(got.astype(np.float64) - r))) <= TOL * max(float(np.max(np.abs(r))), 1e-30)
+        tot = obj.compute_total_loss(dev(golden[f"{c['id']}/y_true"]), dev(golden[f"{c['id']}/y_pred"]))
+        assert rel_err(host(tot), golden[f"{c['id']}/total_loss"]) < TOL
+        obj.flush_logs()
+        assert (tmp_path / "custom_losses" / "total_loss.log").read_text().strip() != ""
+
+
+def test_golden_host_layers(lq, golden):
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.custom_loss_terms.custom_components import custom_layers as cl
+    from learned_quantization_b200.paper_implementation.custom_components import custom_layers as pi
+    mods = {"NQ": nq, "CL": cl, "PI": pi}
+    for c in golden.manifest["layers"]:
+        cid = c["id"]
+        ctor = dict(c["ctor"])
+        for k in ("kernel_size", "strides"):
+            if k in ctor:
+                ctor[k] = tuple(ctor[k])
+        weights = [golden[f"{cid}/w0"]] + ([golden[f"{cid}/w1"]] if f"{cid}/w1" in golden.arrays else [])
+        layer = getattr(mods[c["module"]], c["class"])(**ctor, initializer=None, regularizer=None, trained_weights=weights)
+        x = dev(golden[f"{cid}/x"]).requires_grad_()
+        layer.build(tuple(x.shape), "cuda")
+        qn = [n for n in ("nested_q_w_layer", "nested_q_k_layer", "nested_q_b_layer") if hasattr(layer, n)]
+        with torch.no_grad():
+            for i, n in enumerate(qn):
+                getattr(layer, n).scale.copy_(dev(golden[f"{cid}/s{i}"]))
+        out = layer(x)
+        ref = golden[f"{cid}/out"]
+        assert out.shape == ref.shape, c
+        assert float(np.max(np.abs(host(out) - ref))) <= 2e-5 * max(float(np.max(np.abs(ref))), 1.0), c
+        (out * dev(golden[f"{cid}/G"])).sum().backward()
+        params = [layer.W if hasattr(layer, "W") else layer.kernel] + ([layer.b] if hasattr(layer, "b") else [])
+        for i, p in enumerate(params):
+            r = golden[f"{cid}/dw{i}"]
+            assert float(np.max(np.abs(host(p.grad) - r))) <= 1e-4 * max(float(np.max(np.abs(r))), 1e-30), (c, i)
+        r = golden[f"{cid}/dx"]
+        assert float(np.max(np.abs(host(x.grad) - r))) <= 1e-4 * max(float(np.max(np.abs(r))), 1e-30), c
+        for i, n in enumerate(qn):
+            r = golden[f"{cid}/ds{i}"]
+            got = host(getattr(layer, n).scale.grad)
+            assert got.shape == r.shape
+            # ds depends on dy only through thresholded ratios; dy differs from the fixture in the last bits
+            assert float(np.max(np.abs(got - r))) <= 2e-3 * max(float(np.max(np.abs(r))), 1e-30), (c, n, got, r)
+
+
+# ------------------------------------------------------------------ randomized vs oracle
+LAYOUTS = [
+    # (shape, scale shape) -> exercises ROW/COL regimes, vector/scalar paths, segments, tails
+    ((1, 1, 5000), (1,)), ((3, 3, 64, 128), (1, 1, 64, 1)), ((3, 3, 16, 32), (1, 1, 16, 1)),
+    ((7, 7, 3, 64), (7, 1, 1, 1)), ((7, 7, 3, 64), (1, 7, 1, 1)), ((784, 128), (1, 128)), ((784, 128), (784, 1)),
+    ((128, 10), (1, 10)), ((128, 10), (128, 1)), ((37, 5, 131), (1, 5, 1)), ((9, 6, 4100), (1, 6, 1)),
+    ((2, 3, 10001), (1, 3, 1)), ((1000, 3), (1, 3)), ((513, 7, 2), (1, 7, 1)), ((5,), (1,)), ((1,), (1,)),
+    ((64, 1024), (1, 1024)), ((300, 260, 4), (1, 260, 1)), ((16, 2048, 128), (1, 2048, 1)),
+]
+
+
+@pytest.mark.parametrize("shape,s_shape", LAYOUTS)
+@pytest.mark.parametrize("lam", [0.0, 1e-10, 1e-3, 0.05])
+def test_random_vs_oracle(lq, shape, s_shape, lam):
+    ops = lq.ops
+    rng = np.random.default_rng(abs(hash((shape, s_shape))) % (2 ** 31))
+    P = rng.normal(0, 0.05, size=shape).astype(np.float32)
+    P.reshape(-1)[:: 17] = 0.0
+    s = rng.uniform(5e-3, 2e-2, size=s_shape).astype(np.float32)
+    dy = rng.normal(0, 1e-3, size=shape).astype(np.float32)
+    dy.reshape(-1)[:: 13] = 0.0
+    q_ref, y_ref = o.fq_forward(P, s)
+    _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, lam, accum="fp64")
+    Pd, sd, dyd = dev(P), dev(s), dev(dy)
+    y, codes = ops.fq_fwd(Pd, sd, codes_dtype=torch.int32)
+    assert bits_equal(host(y), y_ref)
+    assert np.array_equal(host(codes), q_ref.astype(np.int32))
+    _, ds = ops.fq_bwd_threshold(dyd, Pd, sd, lam)
+    assert ds_close(host(ds).reshape(ds_ref.shape), ds_ref), (host(ds), ds_ref)
+    _, ds_b = ops.fq_bwd_threshold(dyd, Pd, sd, lam)
+    assert bits_equal(host(ds), host(ds_b)), "second-stage reduction must be deterministic"
+
+
+def test_unaligned_pointers_take_scalar_path(lq):
+    ops = lq.ops
+    rng = np.random.default_rng(5)
+    for shape, s_shape in [((6, 8, 256), (1, 8, 1)), ((100, 12), (1, 12)), ((1, 1, 9000), (1,))]:
+        n = int(np.prod(shape))
+        P = rng.normal(0, 0.05, size=n + 1).astype(np.float32)
+        dy = rng.normal(0, 1e-3, size=n + 1).astype(np.float32)
+        s = rng.uniform(5e-3, 2e-2, size=s_shape).astype(np.float32)
+        Pd, dyd = dev(P)[1:].view(shape), dev(dy)[1:].view(shape)     # 4-byte aligned only
+        assert Pd.data_ptr() % 16 != 0
+        q_ref, y_ref = o.fq_forward(P[1:].reshape(shape), s)
+        _, ds_ref = o.nested_backward(dy[1:].reshape(shape), q_ref, y_ref, s, 1e-3, accum="fp64")
+        y = ops.fq_fwd(Pd, dev(s), out=torch.empty(n + 1, device="cuda")[1:].view(shape))
+        assert bits_equal(host(y), y_ref)
+        _, ds = ops.fq_bwd_threshold(dyd, Pd, dev(s), 1e-3)
+        assert ds_close(host(ds).reshape(ds_ref.shape), ds_ref)
+
+
+def test_special_values(lq):
+    ops = lq.ops
+    P = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-38, -1e-38, 3e38, 0.3, -0.26, 1e-45, -1e-45], np.float32)
+    P = np.tile(P, 20)
+    for sv in (0.1, 1.1920929e-05, 3.0):
+        s = np.array([sv], np.float32)
+        q_ref, y_ref = o.fq_forward(P, s)
+        y, codes = ops.fq_fwd(dev(P), dev(s), codes_dtype=torch.float32)
+        assert bits_equal(host(y), y_ref), sv
+        assert bits_equal(host(codes), q_ref), sv
+    # NaN ratio -> counts as "below" and poisons ds
+    Pn = np.array([0.3, 0.2, -0.1, 0.25] * 40, np.float32)
+    dy = np.zeros_like(Pn)
+    dy[5] = np.nan
+    s = np.array([0.1], np.float32)
+    q_ref, y_ref = o.fq_forward(Pn, s)
+    _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, 1e-3)
+    _, ds = ops.fq_bwd_threshold(dev(dy), dev(Pn), dev(s), 1e-3)
+    assert np.isnan(ds_ref).all() and np.isnan(host(ds)).all()
+
+
+def test_rne_clamp_extension(lq):
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(3)
+    P = rng.normal(0, 0.05, size=(4, 16, 256)).astype(np.float32)
+    s = rng.uniform(5e-3, 2e-2, size=(1, 16, 1)).astype(np.float32)
+    q_ref, y_ref = o.fq_forward(P, s, round_mode=o.ROUND_RNE, qmin=-8, qmax=7)
+    y, codes = ops.fq_fwd(dev(P), dev(s), codes_dtype=torch.int8, round_mode=_lib.LQ_ROUND_RNE, qmin=-8.0, qmax=7.0)
+    assert bits_equal(host(y), y_ref)
+    assert np.array_equal(host(codes), q_ref.astype(np.int8))
+    assert host(codes).min() == -8 and host(codes).max() == 7
+
+
+def test_int8_codes_wrap_like_reference_export(lq):
+    ops = lq.ops
+    rng = np.random.default_rng(4)
+    P = rng.normal(0, 0.05, size=(3, 3, 8, 16)).astype(np.float32)
+    s = np.full((1, 1, 8, 1), o.SCALE_INIT, np.float32)          # init-time codes reach +-2e4
+    _, codes = ops.fq_fwd(dev(P), dev(s), codes_dtype=torch.int8)
+    assert np.array_equal(host(codes), o.codes_int8(P, s))
+
+
+def test_multi_tensor_equals_single(lq):
+    ops = lq.ops
+    rng = np.random.default_rng(11)
+    shapes = [((3, 3, 16, 32), (1, 1, 16, 1)), ((32,), (1,)), ((7, 7, 3, 64), (1, 1, 3, 1)), ((64,), (1,)),
+              ((3, 3, 64, 128), (1, 1, 64, 1)), ((128,), (1,)), ((784, 128), (784, 1)), ((1, 1, 64, 128), (1, 1, 64, 1))]
+    shapes = shapes * 8          # 64 tensors: more than one kernel-parameter table
+    Ps = [dev(rng.normal(0, 0.05, size=sh).astype(np.float32)) for sh, _ in shapes]
+    ss = [dev(rng.uniform(5e-3, 2e-2, size=ssh).astype(np.float32)) for _, ssh in shapes]
+    dys = [dev(rng.normal(0, 1e-3, size=sh).astype(np.float32)) for sh, _ in shapes]
+    ys = [torch.empty_like(p) for p in Ps]
+    dss = [torch.empty_like(s) for s in ss]
+    ops.mt_fq_fwd(Ps, ss, ys)
+    ops.mt_fq_bwd(dys, Ps, ss, dss, 1e-3)
+    for p, s, dy, y, ds in zip(Ps, ss, dys, ys, dss):
+        y1 = ops.fq_fwd(p, s)
+        _, ds1 = ops.fq_bwd_threshold(dy, p, s, 1e-3)
+        assert bits_equal(host(y), host(y1)) and bits_equal(host(ds), host(ds1))
+    dss0 = [torch.ones_like(s) for s in ss]
+    from learned_quantization_b200 import _lib
+    ops.mt_fq_bwd(dys, Ps, ss, dss0, 1e-3, scale_grad_mode=_lib.LQ_SGRAD_NONE)
+    assert all(not host(d).any() for d in dss0)
+
+
+def test_penalties_random_vs_oracle(lq):
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(21)
+    specs = [((3, 3, 64, 128), (1, 1, 64, 1)), ((7, 7, 3, 64), (7, 1, 1, 1)), ((784, 128), (1, 128)),
+             ((3, 3, 128, 256), (1,)), ((37, 5, 131), (1, 5, 1))]
+    layers = []
+    for sh, ssh in specs:
+        K = rng.normal(0, 0.05, size=sh).astype(np.float32)
+        sK = rng.uniform(5e-3, 2e-2, size=ssh).astype(np.float32)
+        b = rng.normal(0, 0.05, size=(sh[-1],)).astype(np.float32)
+        sb = rng.uniform(5e-3, 2e-2, size=(1,)).astype(np.float32)
+        layers.append((K, sK, b, sb))
+    Ps, ss = [], []
+    for K, sK, b, sb in layers:
+        Ps += [dev(K), dev(b)]; ss += [dev(sK), dev(sb)]
+    for kind, val, grad in ((_lib.LQ_PEN_MAXBIN, o.maxbin_penalty, o.maxbin_penalty_grads),
+                            (_lib.LQ_PEN_DIFFERENCE, o.difference_penalty, o.difference_penalty_grads),
+                            (_lib.LQ_PEN_INVERSE, o.inverse_penalty, o.inverse_penalty_grads)):
+        out, ws = ops.penalty_fwd(kind, Ps, ss)
+        assert rel_err(host(out), val(layers)) < TOL, kind
+        dXs, dss = ops.penalty_bwd(kind, Ps, ss, ws, 0.5)
+        ref = grad(layers, 0.5, accum="fp64")
+        flat_ref = []
+        for gK, gsK, gb, gsb in ref:
+            flat_ref += [(gK, gsK), (gb, gsb)]
+        for i, (gP, gs) in enumerate(flat_ref):
+            if kind != _lib.LQ_PEN_INVERSE:
+                assert float(np.max(np.abs(host(dXs[i]).astype(np.float64) - gP))) <= TOL * max(float(np.max(np.abs(gP))), 1e-30), (kind, i)
+            assert float(np.max(np.abs(host(dss[i]).astype(np.float64).reshape(gs.shape) - gs))) <= TOL * max(float(np.max(np.abs(gs))), 1e-30), (kind, i)
+
+
+def test_host_buffer_path_matches_device_path(lq):
+    ops = lq.ops
+    rng = np.random.default_rng(31)
+    for layout in [(64, 512, 512), (1, 1, 9_000_001), (1, 6, 3_000_000), (70000, 64, 1), (3, 5, 7)]:
+        n = layout[0] * layout[1] * layout[2]
+        P = rng.normal(0, 0.05, size=n).astype(np.float32)
+        dy = rng.normal(0, 1e-3, size=n).astype(np.float32)
+        s = rng.uniform(5e-3, 2e-2, size=layout[1]).astype(np.float32)
+        hP, hdy, hs = (torch.from_numpy(a).pin_memory() for a in (P, dy, s))
+        hy = torch.empty(n).pin_memory()
+        hds = torch.empty(layout[1]).pin_memory()
+        ws = torch.empty(ops.host_workspace_bytes(layout), dtype=torch.uint8, device="cuda")
+        ops.host_fq_fwd_bwd(hP, hs, hdy, 1e-3, hy, hds, layout, ws)
+        Pd, sd, dyd = dev(P), dev(s), dev(dy)
+        y = ops.fq_fwd(Pd, sd, layout)
+        _, ds = ops.fq_bwd_threshold(dyd, Pd, sd, 1e-3, layout)
+        assert bits_equal(hy.numpy(), host(y)), layout
+        assert ds_close(hds.numpy(), host(ds)), layout
+
+
+def test_errors_are_loud(lq):
+    from learned_quantization_b200 import LqError, _lib
+    ops = lq.ops
+    P = torch.zeros(4, 4, device="cuda")
+    s = torch.ones(1, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.fq_fwd(P.cpu(), s.cpu())                      # no CPU fallback
+    with pytest.raises(LqError) as e:
+        ops.fq_fwd(P, s, round_mode=7)
+    assert e.value.status == -3
+    with pytest.raises(LqError) as e:
+        ops.fq_fwd(P, s, qmin=3.0, qmax=1.0)
+    assert e.value.status == -3
+    with pytest.raises(ValueError):
+        ops.group_layout((4, 4), (2, 2))
+    rc = _lib.lib.lq_fq_bwd_threshold(P.data_ptr(), P.data_ptr(), s.data_ptr(), 0.0, None, s.data_ptr(),
+                                      1, 1, 16, 0, float("-inf"), float("inf"), None, 0, None)
+    assert rc == -4 and b"workspace" in _lib.lib.lq_last_error()
+    rc = _lib.lib.lq_fq_fwd(None, s.data_ptr(), P.data_ptr(), None, 0, 1, 1, 16, 0, float("-inf"), float("inf"), None)
+    assert rc == -1
+
+
+# ------------------------------------------------------------------ BASELINE full size
+@pytest.mark.parametrize("layout", [(256, 512, 512), (1, 1, 1 << 26), (1 << 17, 512, 1)])
+def test_full_size_64mi_vs_oracle(lq, layout):
+    """The headline configuration (64 Mi elements) against the oracle evaluated on the whole
+    tensor for the forward (bit-exact) and group by group for ds."""
+    ops = lq.ops
+    n = layout[0] * layout[1] * layout[2]
+    g = torch.Generator(device="cuda").manual_seed(42)
+    Pd = torch.randn(n, device="cuda", generator=g) * 0.05
+    dyd = torch.randn(n, device="cuda", generator=g) * 1e-3
+    sd = torch.rand(layout[1], device="cuda", generator=g) * 1.5e-2 + 5e-3
+    y = ops.fq_fwd(Pd, sd, layout)
+    _, ds = ops.fq_bwd_threshold(dyd, Pd, sd, 1e-3, layout)
+    _, ds2 = ops.fq_bwd_threshold(dyd, Pd, sd, 1e-3, layout, write_dx=True)
+    assert bits_equal(host(ds), host(ds2))
+    shape = layout
+    P, dy, s = host(Pd).reshape(shape), host(dyd).reshape(shape), host(sd).reshape(1, layout[1], 1)
+    q_ref, y_ref = o.fq_forward(P, s)
+    assert bits_equal(host(y).reshape(shape), y_ref)
+    _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, 1e-3, accum="fp64")
+    assert ds_close(host(ds).reshape(ds_ref.shape), ds_ref)
