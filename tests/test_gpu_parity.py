@@ -82,7 +82,7 @@ def test_golden_scale_layer_shapes_and_errors(lq, golden):
         layer = nq.CustomQuantizedScaleLayer(penalty_threshold=0.0, initializer=None, orientation=c["orientation"])
         layer.build(tuple(c["param"]), "cuda")
         assert list(layer.scale.shape) == c["scale"], c
-        assert float(layer.scale.flatten()[0]) == 1.1920928955078125e-05
+        assert float(layer.scale.detach().flatten()[0]) == 1.1920928955078125e-05
     bad = nq.CustomQuantizedScaleLayer(penalty_threshold=0.0, initializer=None, orientation="diagonal")
     with pytest.raises(ValueError) as e:
         bad.build((3, 3), "cuda")
@@ -158,6 +158,9 @@ def test_golden_host_layers(lq, golden):
     from learned_quantization_b200.custom_loss_terms.custom_components import custom_layers as cl
     from learned_quantization_b200.paper_implementation.custom_components import custom_layers as pi
     mods = {"NQ": nq, "CL": cl, "PI": pi}
+    # the fixtures are fp32 CPU convolutions; cuDNN would otherwise pick TF32 (conv is not our path)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     for c in golden.manifest["layers"]:
         cid = c["id"]
         ctor = dict(c["ctor"])
