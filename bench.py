@@ -28,6 +28,7 @@ UNIT = "GB/s"
 LAYOUT = (256, 512, 512)          # 64 Mi elements, channelwise C = 512 on an HWIO-like tensor
 LAMBDA = 1e-3                     # ~3% of elements below threshold: both NQ:103-111 branches live
 BYTES_FWD, BYTES_BWD = 8, 12      # algorithmic bytes per element (SURVEY 8d / BASELINE.md 3)
+WORKLOAD = "fakequant_fwd_bwd_channelwise_C512_inner512"
 
 
 def synth(layout, seed, numpy=False):
@@ -94,38 +95,60 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------- CPU arms
+# The reference's own CPU path is TensorFlow-CPU running the un-fused op chain of NQ:55-118;
+# TensorFlow is not installable here, so the timed stand-in is oracle/lq_oracle.c: the same
+# chain (one pass + one materialised temporary per reference op), OpenMP over all host cores.
+_CO = None
+
+
+def cpu_oracle():
+    global _CO
+    if _CO is None:
+        from oracle import lq_oracle_c
+        _CO = lq_oracle_c.COracle()
+    return _CO
+
+
 def cpu_oracle_step(P, s, dy, layout, lam):
-    """One fwd+bwd of the oracle port (oracle/lq_oracle.py, un-fused op chain like NQ:55-118)."""
-    from oracle import lq_oracle as o
-    shape = layout
-    q, y = o.fq_forward(P.reshape(shape), s.reshape(1, layout[1], 1))
-    _, ds = o.nested_backward(dy.reshape(shape), q, y, s.reshape(1, layout[1], 1), lam)
-    return y, ds
+    return cpu_oracle().fwd_bwd(P, s, dy, layout, lam)
 
 
-def cpu_baseline(sample_outer, reps=1):
+def cpu_sample(sample_outer):
     layout = (sample_outer, LAYOUT[1], LAYOUT[2])
     P, s, dy = synth(layout, 42)
-    n = P.size
-    cpu_oracle_step(P[: n // 8], s, dy[: n // 8], (max(sample_outer // 8, 1), layout[1], layout[2]), LAMBDA)  # warm
+    return layout, P, s, dy
+
+
+def cpu_describe(layout, n, dt):
+    co = cpu_oracle()
+    return {"unit": UNIT, "cores": co.threads, "kind": "port",
+            "sample": f"oracle/lq_oracle.c (reference op chain NQ:55-118, OpenMP x{co.threads}) fwd+bwd on "
+                      f"[{layout[0]},{layout[1]},{layout[2]}] = {n} elements of the workload, {dt * 1e3:.1f} ms per pass",
+            "host_cpus": os.cpu_count()}
+
+
+def cpu_baseline(sample_outer=32, budget_s=12.0):
+    layout, P, s, dy = cpu_sample(sample_outer)
+    cpu_oracle_step(P, s, dy, layout, LAMBDA)          # warm (page faults, thread pool)
     t0 = time.perf_counter()
-    for _ in range(reps):
+    reps = 0
+    while True:
         cpu_oracle_step(P, s, dy, layout, LAMBDA)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 200:
+            break
     dt = (time.perf_counter() - t0) / reps
-    return {"value": (BYTES_FWD + BYTES_BWD) * n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle/lq_oracle.py (numpy, single thread) fwd+bwd on [{layout[0]},{layout[1]},{layout[2]}] "
-                      f"= {n} elements of the workload, {dt:.2f} s",
-            "host_cpus": os.cpu_count()}, dt
+    cb = cpu_describe(layout, P.size, dt)
+    cb["value"] = (BYTES_FWD + BYTES_BWD) * P.size / dt / 1e9
+    return cb
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_outer = 8      # 2 Mi elements per step
-    cb, _ = cpu_baseline(sample_outer)
-    layout = (sample_outer, LAYOUT[1], LAYOUT[2])
-    P, s, dy = synth(layout, 42)
+    sample_outer = 32     # 8 Mi elements per step
+    layout, P, s, dy = cpu_sample(sample_outer)
     for _ in range(args.warmup):
         cpu_oracle_step(P, s, dy, layout, LAMBDA)
     t0 = time.perf_counter()
@@ -133,14 +156,16 @@ def run_reference(args):
         cpu_oracle_step(P, s, dy, layout, LAMBDA)
     dt = time.perf_counter() - t0
     val = (BYTES_FWD + BYTES_BWD) * P.size * args.steps / dt / 1e9
+    cb = cpu_describe(layout, P.size, dt / args.steps)
     cb["value"] = val
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "fakequant_fwd_bwd_channelwise_C512_inner512", "layout": list(LAYOUT),
+        "config": {"workload": WORKLOAD, "layout": list(LAYOUT),
                    "lambda": LAMBDA, "step": f"bounded sample [{sample_outer},512,512] of the 64Mi-element tensor",
-                   "note": "reference CPU path = TensorFlow-CPU (not installable); timed stand-in is the op-for-op oracle port"},
+                   "note": "reference CPU path = TensorFlow-CPU (not installable); timed stand-in is the op-for-op C port"},
+        "elements_per_s": P.size * args.steps / dt,
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -238,12 +263,12 @@ def run_ours(args):
         value = (BYTES_FWD + BYTES_BWD) * n * world / (step_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         achieved = BYTES_BWD * n / (bwd_ms * 1e-3) / 1e9
-        cb, _ = cpu_baseline(32) if world == 1 else (None, None)
+        cb = cpu_baseline() if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "fakequant_fwd_bwd_channelwise_C512_inner512", "layout": list(LAYOUT),
+            "config": {"workload": WORKLOAD, "layout": list(LAYOUT),
                        "elements_per_gpu": n, "lambda": LAMBDA, "l2": "inputs_exceed_l2 (3 x 256 MiB arrays per pass, 2 input sets alternated)",
                        "bytes_per_element": {"fwd": BYTES_FWD, "bwd": BYTES_BWD}, "dX": "written (not aliased to dy)"},
             "elements_per_s": n * world / (step_ms * 1e-3),

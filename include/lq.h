@@ -135,6 +135,14 @@ int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float* hdy, float
                        int64_t outer, int64_t C, int64_t inner,
                        void* dev_ws, size_t dev_ws_bytes);
 
+/* Diagnostics: checks on the device that the kernels' hoisted-reciprocal division equals
+ * IEEE division (the bit-exactness the forward is graded on, NQ:56-58 tf.truediv) for every
+ * 23-bit mantissa of the dividend a = bits(a_sign_exp_bits | mantissa) against each divisor
+ * s_bits[i] (n_s <= 2^24).  out3 (device, zeroed by the caller) accumulates
+ * {mismatches, pairs checked inside the fast window, first mismatching (a<<32 | s)}. */
+int lq_debug_divcheck(const uint32_t* s_bits, int64_t n_s, uint32_t a_sign_exp_bits,
+                      unsigned long long* out3, lq_stream_t stream);
+
 /* Data parallelism (new; the reference is single-device, experiment.py:774-788):
  * one NCCL communicator per process, sum-allreduce of a flat fp32 gradient bucket scaled
  * by `scale` (1/world) in the same call. */

@@ -10,14 +10,15 @@ namespace lq {
 // --------------------------------------------------------------- element operators
 // MaxBin forward: per group max_j(|P_j| / s) and how many elements attain it (the tie
 // count _MinOrMaxGrad divides by).  acc.c = max, acc.b = ties.
-struct MaxBinStatOp {
+struct MaxBinStatOp : OpBase<MaxBinStatOp> {
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = -1.f; }
   __device__ static void combine(Acc& x, const Acc& y) {
     if (y.c > x.c) { x.c = y.c; x.b = y.b; }
     else if (y.c == x.c) x.b += y.b;
   }
-  __device__ __forceinline__ void elem(float p, float, float s, const float4&, const Job&, Acc& acc, float&, float&) const {
+  __device__ __forceinline__ void elem(float p, float, const PlainCtx& c, const Job&, Acc& acc, float&, float&) const {
+    const float s = c.s;
     const float d = __fdiv_rn(fabsf(p), s);          // LF:92 tf.abs(kernel) / kernel_scale
     if (d > acc.c) { acc.c = d; acc.b = 1u; }
     else if (d == acc.c) acc.b += 1u;
@@ -25,11 +26,12 @@ struct MaxBinStatOp {
 };
 
 // Difference forward: sum_j |P_j - P_j / s|  (LF:175-178, un-floored quotient). acc.a = sum.
-struct DiffStatOp {
+struct DiffStatOp : OpBase<DiffStatOp> {
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
-  __device__ __forceinline__ void elem(float p, float, float s, const float4&, const Job&, Acc& acc, float&, float&) const {
+  __device__ __forceinline__ void elem(float p, float, const PlainCtx& c, const Job&, Acc& acc, float&, float&) const {
+    const float s = c.s;
     acc.a += fabsf(__fsub_rn(p, __fdiv_rn(p, s)));
   }
 };
@@ -39,12 +41,14 @@ __device__ __forceinline__ float sgn(float x) { return (float)((x > 0.f) - (x < 
 // MaxBin backward w.r.t. P: aux = {mb_g, ties, coef_g = (1/ties) * g_mb}.
 //   g_d = indicator(d == mb) * coef ; g_a = g_d / s ; g_P = g_a * sign(P)
 template <bool ACCUM>
-struct MaxBinBwdOp {
+struct MaxBinBwdOp : OpBase<MaxBinBwdOp<ACCUM>> {
   const float* up;   // effective upstream (device scalar); already folded into aux.z
   static constexpr bool kIn2 = ACCUM, kOutIsY = false, kCodes = false, kReduce = false, kAux = true;
   __device__ static void init(Acc&) {}
   __device__ static void combine(Acc&, const Acc&) {}
-  __device__ __forceinline__ void elem(float p, float old, float s, const float4& aux, const Job&, Acc&, float& dx, float&) const {
+  __device__ __forceinline__ void elem(float p, float old, const PlainCtx& c, const Job&, Acc&, float& dx, float&) const {
+    const float s = c.s;
+    const float4& aux = c.aux;
     const float d = __fdiv_rn(fabsf(p), s);
     const float g_d = (d == aux.x) ? aux.z : 0.f;
     const float g = __fmul_rn(__fdiv_rn(g_d, s), sgn(p));
@@ -55,12 +59,13 @@ struct MaxBinBwdOp {
 // Difference backward: d = P - P/s ; g_d = g_abs * sign(d)
 //   g_P = g_d + (-g_d)/s ;  ds_g += (-g_d) * ((-P / s) / s)      (job.t0 = g_abs)
 template <bool ACCUM>
-struct DiffBwdOp {
+struct DiffBwdOp : OpBase<DiffBwdOp<ACCUM>> {
   const float* up;   // effective upstream (device scalar)
   static constexpr bool kIn2 = ACCUM, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
-  __device__ __forceinline__ void elem(float p, float old, float s, const float4&, const Job& j, Acc& acc, float& dx, float&) const {
+  __device__ __forceinline__ void elem(float p, float old, const PlainCtx& c, const Job& j, Acc& acc, float& dx, float&) const {
+    const float s = c.s;
     const float pq = __fdiv_rn(p, s);
     const float g_d = __fmul_rn(__fmul_rn(j.t0, __ldg(up)), sgn(__fsub_rn(p, pq)));
     const float g = __fadd_rn(g_d, __fdiv_rn(-g_d, s));
@@ -68,6 +73,8 @@ struct DiffBwdOp {
     dx = ACCUM ? __fadd_rn(old, g) : g;
   }
 };
+
+template <class Op> static Op make_pen_op(const float* up) { Op op; op.up = up; return op; }
 
 // --------------------------------------------------------------- second stages
 enum { PFIN_MAXBIN = 1, PFIN_SUM = 2, PFIN_SUM_DS = 3 };
@@ -373,8 +380,8 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
       if ((rc = cuda_fail(cudaGetLastError(), "penalty group launch"))) break;
     }
     if (tab.n) {
-      if (kind == LQ_PEN_MAXBIN) rc = accum ? launch_mt(tab, MaxBinBwdOp<true>{up}, st) : launch_mt(tab, MaxBinBwdOp<false>{up}, st);
-      else rc = accum ? launch_mt(tab, DiffBwdOp<true>{up}, st) : launch_mt(tab, DiffBwdOp<false>{up}, st);
+      if (kind == LQ_PEN_MAXBIN) rc = accum ? launch_mt(tab, make_pen_op<MaxBinBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<MaxBinBwdOp<false>>(up), st);
+      else rc = accum ? launch_mt(tab, make_pen_op<DiffBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<DiffBwdOp<false>>(up), st);
       if (rc) break;
       if (fin.n) {
         pen_finalize_kernel<<<dim3(groups), dim3(kFinThreads), 0, st>>>(fin);

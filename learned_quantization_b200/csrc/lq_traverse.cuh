@@ -6,7 +6,13 @@
 //   static constexpr bool kCodes    out1 is the integer code, written to Job::codes if set
 //   static constexpr bool kReduce   per-unit partials are produced
 //   static constexpr bool kAux      per-group float4 Job::gaux[g] is fetched next to the scale
-//   elem(p, in2, s, aux, job, acc, out0, out1)
+//   Ctx prep(s, aux)                 per-(thread, group) constants, hoisted out of the element loop
+//   elem(p, in2, ctx, job, acc, out0, out1)
+//   quad(p4, in2_4, ctx, job, acc, out0_4, out1_4, defer)   four consecutive elements of one
+//                                    group (ROW, 128-bit path); OpBase supplies it as 4 x elem
+//   static constexpr int kDeferSlots  per-thread queue entries (float2) in shared memory that quad()
+//                                    may push rare-case work to; flush(acc, defer) drains them once per
+//                                    16 elements with the warp converged (0 = unused)
 #pragma once
 #include "lq_common.cuh"
 
@@ -22,6 +28,29 @@ __device__ __forceinline__ float4 pack_acc(const Acc& x) {
 __device__ __forceinline__ Acc unpack_acc(const float4& v) {
   Acc x; x.a = v.x; x.b = __float_as_uint(v.y); x.c = v.z; return x;
 }
+
+// Default per-group context (scale + optional aux operands) and default quad.
+struct PlainCtx { float s; float4 aux; };
+// A thread's private rare-case queue: entry k lives at slot[k * 32] (lane-interleaved inside the
+// warp's region, so a warp-wide push or pop of the same k is bank-conflict free).  Only the
+// owning thread ever touches its entries: no synchronisation is involved.
+struct Defer { float2* slot; int n; };
+template <class D>
+struct OpBase {
+  using Ctx = PlainCtx;
+  static constexpr int kDeferSlots = 0;
+  __device__ __forceinline__ PlainCtx prep(float s, const float4& aux) const { return PlainCtx{s, aux}; }
+  __device__ __forceinline__ void flush(Acc&, Defer&) const {}
+  template <class C>
+  __device__ __forceinline__ void quad(const float4& p, const float4& d, const C& c, const Job& j, Acc& acc,
+                                       float4& o, float4& q, Defer&) const {
+    const D& self = *static_cast<const D*>(this);
+    self.elem(p.x, d.x, c, j, acc, o.x, q.x);
+    self.elem(p.y, d.y, c, j, acc, o.y, q.y);
+    self.elem(p.z, d.z, c, j, acc, o.z, q.z);
+    self.elem(p.w, d.w, c, j, acc, o.w, q.w);
+  }
+};
 
 template <class Op>
 __device__ __forceinline__ Acc warp_reduce_acc(Acc x) {
@@ -44,15 +73,15 @@ __device__ __forceinline__ void store_code(void* codes, int dtype, long long idx
 
 // ------------------------------------------------------------------------- ROW regime
 template <class Op, bool STREAM, bool VEC>
-__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op) {
+__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op, float2* queue) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
   if (unit >= j.units) return;
   const long long row = unit / j.nseg;
   const int sg = (int)(unit - row * j.nseg);
   const long long grp = row % j.C;
-  const float s = __ldg(j.s + grp);
-  const float4 aux = Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const typename Op::Ctx ctx = op.prep(__ldg(j.s + grp),
+                                       Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
   const long long base = row * j.inner + (long long)sg * j.seg;
   const long long rem = j.inner - (long long)sg * j.seg;
   const int len = rem < j.seg ? (int)rem : j.seg;
@@ -60,6 +89,9 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
   Acc acc; Op::init(acc);
   float* out = Op::kOutIsY ? j.y : j.dX;
   const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
+  Defer df;
+  df.slot = queue + (threadIdx.x >> 5) * (Op::kDeferSlots * 32) + lane;
+  df.n = 0;
 
   if constexpr (VEC) {
     const int nvec = len >> 2;
@@ -81,10 +113,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         const int v = v0 + u * 32 + lane;
         if (v < nvec) {
           float4 o, c;
-          op.elem(p[u].x, Op::kIn2 ? d[u].x : 0.f, s, aux, j, acc, o.x, c.x);
-          op.elem(p[u].y, Op::kIn2 ? d[u].y : 0.f, s, aux, j, acc, o.y, c.y);
-          op.elem(p[u].z, Op::kIn2 ? d[u].z : 0.f, s, aux, j, acc, o.z, c.z);
-          op.elem(p[u].w, Op::kIn2 ? d[u].w : 0.f, s, aux, j, acc, o.w, c.w);
+          op.quad(p[u], Op::kIn2 ? d[u] : make_float4(0.f, 0.f, 0.f, 0.f), ctx, j, acc, o, c, df);
           if (wr) st4<STREAM>(O4 + v, o);
           if (Op::kCodes && j.codes) {
             const long long e = base + 4ll * v;
@@ -95,6 +124,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
           }
         }
       }
+      if (Op::kDeferSlots) op.flush(acc, df);   // warp is converged here (v0 loop is warp-uniform)
     }
   } else {
     for (int e0 = 0; e0 < len; e0 += 128) {
@@ -112,7 +142,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         const int e = e0 + u * 32 + lane;
         if (e < len) {
           float o, c;
-          op.elem(p[u], Op::kIn2 ? d[u] : 0.f, s, aux, j, acc, o, c);
+          op.elem(p[u], Op::kIn2 ? d[u] : 0.f, ctx, j, acc, o, c);
           if (wr) st1<STREAM>(out + base + e, o);
           if (Op::kCodes && j.codes) store_code(j.codes, j.codes_dtype, base + e, c);
         }
@@ -140,15 +170,14 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   const long long r0 = chunk * j.rpc;
   const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
 
-  float s[V];
-  float4 aux[V];
+  typename Op::Ctx ctx[V];
   Acc acc[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     Op::init(acc[k]);
     const long long grp = active ? (col0 + k) / j.inner : 0;
-    s[k] = active ? __ldg(j.s + grp) : 1.0f;
-    aux[k] = (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ctx[k] = op.prep(active ? __ldg(j.s + grp) : 1.0f,
+                     (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
   float* out = Op::kOutIsY ? j.y : j.dX;
   const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
@@ -183,7 +212,7 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
           float o[V], c[V];
 #pragma unroll
           for (int k = 0; k < V; ++k)
-            op.elem(p[u][k], Op::kIn2 ? d[u][k] : 0.f, s[k], aux[k], j, acc[k], o[k], c[k]);
+            op.elem(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc[k], o[k], c[k]);
           if (wr) {
             if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(out + e), make_float4(o[0], o[1], o[2], o[3]));
             else st1<STREAM>(out + e, o[0]);
@@ -228,15 +257,25 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 
 template <class Op, bool STREAM, bool VEC>
 __device__ __forceinline__ void run_job(const Job& j, unsigned blk, const Op& op, Acc* smem) {
-  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op);
+  // ROW and COL never share a block, so the defer queue and the COL tree use the same bytes
+  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op, reinterpret_cast<float2*>(smem));
   else run_col<Op, STREAM, VEC>(j, blk, op, smem);
 }
 
 // Single-tensor kernels: the Job travels in the kernel parameters.  One instantiation per
 // regime so that each keeps only its own registers (the ROW kernel is the bandwidth path).
+template <class Op>
+struct SmemPlan {
+  static constexpr int kQueueEntries = Op::kDeferSlots ? Op::kDeferSlots * kThreads : 1;
+  static constexpr int kColBytes = Op::kReduce ? 4 * kThreads * (int)sizeof(Acc) : 16;
+  static constexpr int kRowBytes = kQueueEntries * (int)sizeof(float2);
+  static constexpr int kMtBytes = kColBytes > kRowBytes ? kColBytes : kRowBytes;
+};
+
 template <class Op, bool STREAM, bool VEC>
 __global__ void __launch_bounds__(kThreads) row_kernel(const __grid_constant__ Job j, const Op op) {
-  run_row<Op, STREAM, VEC>(j, blockIdx.x, op);
+  __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
+  run_row<Op, STREAM, VEC>(j, blockIdx.x, op, queue);
 }
 template <class Op, bool STREAM, bool VEC>
 __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ Job j, const Op op) {
@@ -247,7 +286,8 @@ __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ J
 // Multi-tensor kernel: block -> tensor by binary search over block_begin.
 template <class Op>
 __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
-  __shared__ Acc smem[Op::kReduce ? 4 * kThreads : 1];
+  __shared__ __align__(16) unsigned char smem_raw[SmemPlan<Op>::kMtBytes];
+  Acc* smem = reinterpret_cast<Acc*>(smem_raw);
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;

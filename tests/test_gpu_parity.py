@@ -227,6 +227,45 @@ def test_random_vs_oracle(lq, shape, s_shape, lam):
     assert bits_equal(host(ds), host(ds_b)), "second-stage reduction must be deterministic"
 
 
+def divcheck(lq, s_bits, a_sign_exp_bits):
+    """(mismatches, pairs checked, first bad pair) of the kernels' hoisted-reciprocal division
+    vs __fdiv_rn over all 2^23 dividend mantissas for every divisor in s_bits."""
+    from learned_quantization_b200._lib import lib, check
+    sb = torch.as_tensor(np.asarray(s_bits, np.uint32).view(np.int32)).cuda()
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    check(lib.lq_debug_divcheck(sb.data_ptr(), sb.numel(), int(a_sign_exp_bits), out.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream))
+    return [int(v) for v in out.cpu()]
+
+
+def test_hoisted_reciprocal_division_is_ieee_division(lq):
+    """The forward is graded bit-exact against tf.truediv (NQ:56-58): the per-group reciprocal
+    fast path must give the IEEE quotient for every dividend mantissa.  4096 divisors (random
+    mantissas and exponents inside the fast window, plus the structured mantissas that are
+    hard for reciprocal-based division) x 2^23 dividend mantissas x 4 dividend exponents/signs."""
+    rng = np.random.default_rng(123)
+    mant = rng.integers(0, 1 << 23, size=4096, dtype=np.uint32)
+    special = np.array([0, 1, 2, 3, 0x7fffff, 0x7ffffe, 0x400000, 0x400001, 0x3fffff, 0x555555, 0x2aaaaa,
+                        0x7ffff0, 0x000fff, 0x600000, 0x200000, 0x100000], np.uint32)
+    mant[:special.size] = special
+    exp = rng.integers(127 - 40, 127 + 40, size=4096, dtype=np.uint32)       # |s| in [2^-40, 2^40)
+    exp[:special.size] = 127
+    sign = (rng.integers(0, 2, size=4096, dtype=np.uint32) << 31)
+    sign[:special.size] = 0
+    s_bits = sign | (exp << 23) | mant
+    total = 0
+    for a_hi in (127 << 23, 126 << 23, (1 << 31) | (130 << 23), (127 - 75) << 23):
+        bad, seen, first = divcheck(lq, s_bits, a_hi)
+        assert bad == 0, f"{bad} mismatches, first a|s = {first:#018x}"
+        total += seen
+    assert total == 4 * 4096 * (1 << 23)
+    # outside the window nothing takes the fast path (and so nothing is counted)
+    bad, seen, _ = divcheck(lq, np.array([0x00000001, 0x7f000000, 0, 0x7f800000], np.uint32), 127 << 23)
+    assert (bad, seen) == (0, 0)
+    bad, seen, _ = divcheck(lq, s_bits[:16], 0)            # denormal / zero dividends
+    assert (bad, seen) == (0, 0)
+
+
 def test_unaligned_pointers_take_scalar_path(lq):
     ops = lq.ops
     rng = np.random.default_rng(5)
