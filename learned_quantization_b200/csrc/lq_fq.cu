@@ -197,7 +197,11 @@ __device__ __forceinline__ void finalize_group(const FinJob& f, long long g) {
   }
 }
 
+// Launched with programmatic stream serialisation (launch_after below): the grid may start
+// while the element kernel drains; griddepcontrol.wait holds it until that kernel has
+// completed and its partials are visible.
 __global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinJob f) {
+  cudaGridDependencySynchronize();
   finalize_group(f, blockIdx.x);
 }
 
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(kFinThreads) mt_finalize_kernel(const __grid_c
     if (tab.job[mid].group_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const FinJob& f = tab.job[lo];
+  cudaGridDependencySynchronize();
   finalize_group(f, blockIdx.x - f.group_begin);
 }
 
@@ -223,6 +228,8 @@ Job make_job(const Geom& g, const float* P, const float* s, const float* dy, flo
   j.stream_hint = (g.n * 4 > kStreamBytes) ? 1 : 0;
   j.write_dx = (dX != nullptr && dX != dy) ? 1 : 0;
   j.block_begin = 0; j.nblocks = (unsigned)g.nblocks;
+  j.fast32 = (g.regime == REG_ROW && g.units < (1ll << 31) && g.C < (1ll << 31)) ? 1 : 0;
+  if (j.fast32) { j.fd_nseg = make_fastdiv((unsigned long long)g.nseg); j.fd_C = make_fastdiv((unsigned long long)g.C); }
   return j;
 }
 
@@ -254,8 +261,7 @@ int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const
 
 int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st) {
   FinJob f = make_fin(g, part, ds, s, lam);
-  finalize_kernel<<<dim3((unsigned)g.C), dim3(kFinThreads), 0, st>>>(f);
-  return cuda_fail(cudaGetLastError(), "finalize launch");
+  return launch_after(finalize_kernel, dim3((unsigned)g.C), dim3(kFinThreads), st, "finalize launch", f);
 }
 
 int check_blocks(const Geom& g) {
@@ -399,8 +405,7 @@ extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_th
     if (qm.ext) rc = launch_mt(tab, make_bwd_op<true>(qm, penalty_threshold), st);
     else rc = launch_mt(tab, make_bwd_op<false>(qm, penalty_threshold), st);
     if (rc) return rc;
-    mt_finalize_kernel<<<dim3(groups), dim3(kFinThreads), 0, st>>>(fin);
-    if ((rc = cuda_fail(cudaGetLastError(), "mt finalize launch"))) return rc;
+    if ((rc = launch_after(mt_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "mt finalize launch", fin))) return rc;
   }
   return LQ_OK;
 }

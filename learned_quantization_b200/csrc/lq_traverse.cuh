@@ -77,9 +77,18 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
   if (unit >= j.units) return;
-  const long long row = unit / j.nseg;
-  const int sg = (int)(unit - row * j.nseg);
-  const long long grp = row % j.C;
+  long long row, grp;
+  int sg;
+  if (j.fast32) {
+    const unsigned r = fd_div((unsigned)unit, j.fd_nseg);
+    sg = (int)((unsigned)unit - r * (unsigned)j.nseg);
+    grp = r - fd_div(r, j.fd_C) * (unsigned)j.C;
+    row = r;
+  } else {
+    row = unit / j.nseg;
+    sg = (int)(unit - row * j.nseg);
+    grp = row % j.C;
+  }
   const typename Op::Ctx ctx = op.prep(__ldg(j.s + grp),
                                        Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
   const long long base = row * j.inner + (long long)sg * j.seg;
@@ -319,6 +328,20 @@ int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float
 int check_blocks(const Geom& g);
 Job make_job(const Geom& g, const float* P, const float* s, const float* dy, float* y, float* dX,
              void* codes, int codes_dtype, float4* part);
+
+// Launch a second-stage kernel with programmatic dependent launch: its launch latency overlaps
+// the tail of the preceding kernel in the stream; the kernel itself must call
+// cudaGridDependencySynchronize() before touching that kernel's output.
+template <class... KArgs, class... Args>
+int launch_after(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cuda_fail(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...), what);
+}
 
 template <class Op>
 int launch_job(const Job& j, const Op& op, cudaStream_t st) {
