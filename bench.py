@@ -86,6 +86,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed ncu --set full capture summary (profiles/traffic.json); None when absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        return t["traffic_bytes_per_launch"] if t.get("workload") == WORKLOAD else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -276,7 +288,8 @@ def run_ours(args):
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_kernel, 512 blocks)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": None},
+                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": ncu_traffic(),
+                         "algorithmic_bytes_per_launch": BYTES_BWD * n},
             "e2e": {"value": (BYTES_FWD + BYTES_BWD) * n * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n + 4 * LAYOUT[1],
                     "d2h_bytes_per_step": 4 * n + 4 * LAYOUT[1],
@@ -291,16 +304,91 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------- layout sweep
+def sweep_layouts():
+    """BASELINE configs[3] / SURVEY 8d: per-tensor and per-channel layouts, 1 Mi .. 1 Gi elements."""
+    out = []
+    for lg in (20, 22, 24, 26, 28, 30):
+        n = 1 << lg
+        out.append(("per_tensor", (1, 1, n)))
+        for c in (64, 512, 2048):
+            if n // (512 * c) >= 1:
+                out.append((f"hwio_like_C{c}", (n // (512 * c), c, 512)))
+            out.append((f"rows_C{c}", (1, c, n // c)))
+            out.append((f"interleaved_C{c}", (n // c, c, 1)))
+    return out
+
+
+def run_sweep(args):
+    """Not the headline: one JSON line per (layout, size) with fwd/bwd device times (median of
+    --steps launches each, CUDA events), written to stdout; arrays rotate so that the working
+    set of consecutive launches exceeds L2."""
+    import torch
+    import learned_quantization_b200 as lq
+    ops, lib, check = lq.ops, lq._lib.lib, lq._lib.check
+    torch.cuda.set_device(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    ninf, pinf = float("-inf"), float("inf")
+    peak, _ = measured_peak()
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    only = set(args.only.split(",")) if args.only else None
+    for name, layout in sweep_layouts():
+        n = layout[0] * layout[1] * layout[2]
+        if n > args.max_elems or (only and name not in only):
+            continue
+        nsets = max(2, min(16, -(-(600 << 20) // (12 * n))))
+        s = torch.empty(layout[1], device="cuda").uniform_(5e-3, 2e-2, generator=gen)
+        Ps = [torch.empty(n, device="cuda").normal_(0, 0.05, generator=gen) for _ in range(nsets)]
+        dys = [torch.empty(n, device="cuda").normal_(0, 1e-3, generator=gen) for _ in range(nsets)]
+        outs = [torch.empty(n, device="cuda") for _ in range(nsets)]
+        ds = torch.empty(layout[1], device="cuda")
+        ws = torch.empty(max(ops.workspace_bytes([ops.make_desc(layout=layout)], lq._lib.LQ_PHASE_BWD), 256),
+                         dtype=torch.uint8, device="cuda")
+
+        def fwd(i):
+            check(lib.lq_fq_fwd(Ps[i].data_ptr(), s.data_ptr(), outs[i].data_ptr(), None, 0, *layout, 0, ninf, pinf, stream))
+
+        def bwd(i):
+            check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), LAMBDA, outs[i].data_ptr(),
+                                          ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+
+        res = {}
+        for tag, fn in (("fwd", fwd), ("bwd", bwd)):
+            for i in range(max(args.warmup, 3)):
+                fn(i % nsets)
+            torch.cuda.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for i, (a, b) in enumerate(evs):
+                a.record(); fn(i % nsets); b.record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in evs)
+            res[tag] = ts[len(ts) // 2]
+        gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
+        print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "rotating_sets": nsets,
+                          "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
+                          "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),
+                          "fwd_bwd_GBps": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9,
+                          "frac_of_measured_peak": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9 / peak}),
+              flush=True)
+        del Ps, dys, outs
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweep", action="store_true", help="layout/size sweep (one JSON line each) instead of the headline")
+    ap.add_argument("--max-elems", type=int, default=1 << 28)
+    ap.add_argument("--only", default="", help="comma-separated layout names for --sweep")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

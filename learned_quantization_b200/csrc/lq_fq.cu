@@ -135,6 +135,40 @@ struct BwdThresholdOp : OpBase<BwdThresholdOp<EXT>> {
     }
     df.n = 0;
   }
+  // COL traversal: a thread's queue mixes its (up to four) columns, i.e. groups; the column
+  // index travels in the two sign bits the division does not use (|dy| and |nz|).
+  __device__ __forceinline__ void elem_k(float p, float dy, const Recip& c, const Job&, Acc* acc, int k,
+                                         float& dx, float&, Defer& df) const {
+    dx = dy;
+    if (c.fast && fast_range(p)) {
+      const float q = round_code<EXT>(div_fast(p, c), qm);
+      const float y = __fmul_rn(q, c.s);
+      const float nz = (y == 0.0f) ? kEps : y;
+      acc[k].c = fmaxf(acc[k].c, fabsf(q));
+      if (!(fabsf(dy) >= __fmul_rn(fabsf(nz), lam_hi))) {
+        df.slot[df.n * 32] = make_float2(__uint_as_float((__float_as_uint(dy) & 0x7fffffffu) | ((unsigned)(k & 1) << 31)),
+                                         __uint_as_float((__float_as_uint(nz) & 0x7fffffffu) | ((unsigned)(k >> 1) << 31)));
+        ++df.n;
+      }
+    } else {
+      slow(p, dy, c.s, acc[k]);
+    }
+  }
+  __device__ __forceinline__ void flush_k(Acc* acc, Defer& df) const {
+    const int m = __reduce_max_sync(0xffffffffu, df.n);
+    for (int i = 0; i < m; ++i) {
+      if (i < df.n) {
+        const float2 e = df.slot[i * 32];
+        const int k = (int)(__float_as_uint(e.x) >> 31) | ((int)(__float_as_uint(e.y) >> 31) << 1);
+        Acc one; one.a = 0.f; one.b = 0u; one.c = 0.f;
+        below(__fdiv_rn(fabsf(e.x), fabsf(e.y)), one);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (kk == k) { acc[kk].a += one.a; acc[kk].b += one.b; }
+      }
+    }
+    df.n = 0;
+  }
   __device__ __forceinline__ void quad(const float4& p, const float4& d, const Recip& c, const Job&, Acc& acc,
                                        float4& dx, float4&, Defer& df) const {
     if (c.fast && fast_range4(p)) {
@@ -162,8 +196,50 @@ static BwdThresholdOp<EXT> make_bwd_op(const QMode& qm, float lam) {
 // thread->partial assignment, then a fixed shuffle/shared-memory tree: deterministic.
 enum { FIN_THRESHOLD = 0 };
 
+// Intermediate level for groups with very many first-level partials (per-tensor scales on
+// large tensors: one group, N/2048 partials): block (g, m) folds partials [m*kFinChunk,
+// (m+1)*kFinChunk) of group g into lin[g*nlin + m] in a fixed order; the last level then
+// reads REG_LIN partials.  Same {sum, count, max} format, fp64 accumulation inside the block.
+__global__ void __launch_bounds__(256) fold_partials_kernel(const __grid_constant__ FinJob f) {
+  cudaGridDependencySynchronize();
+  const long long g = blockIdx.x / f.nlin, m = blockIdx.x - g * f.nlin;
+  const long long K = partials_per_group(f);
+  const long long k0 = m * kFinChunk;
+  double sum = 0.0;
+  unsigned cnt = 0u;
+  float mx = 0.f;
+  float4 v[kFinChunk / 256];
+#pragma unroll
+  for (int u = 0; u < kFinChunk / 256; ++u) {
+    const long long k = k0 + u * 256 + threadIdx.x;
+    v[u] = (k < K) ? f.part[partial_index(f, g, k)] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < kFinChunk / 256; ++u) {
+    sum += (double)v[u].x; cnt += __float_as_uint(v[u].y); mx = fmaxf(mx, v[u].z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double ssum[8];
+  __shared__ unsigned scnt[8];
+  __shared__ float smx[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; scnt[w] = cnt; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = ssum[0]; cnt = scnt[0]; mx = smx[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { sum += ssum[i]; cnt += scnt[i]; mx = fmaxf(mx, smx[i]); }
+    f.lin[blockIdx.x] = make_float4((float)sum, __uint_as_float(cnt), mx, 0.f);
+  }
+}
+
 __device__ __forceinline__ void finalize_group(const FinJob& f, long long g) {
-  const long long K = (f.regime == REG_ROW) ? f.outer * f.nseg : f.nchunks * f.inner;
+  const long long K = partials_per_group(f);
   double sum = 0.0;
   unsigned long long cnt = 0ull;
   float mx = 0.f;
@@ -237,6 +313,7 @@ static FinJob make_fin(const Geom& g, const float4* part, float* ds, const float
   FinJob f{};
   f.part = part; f.ds = ds; f.s = s;
   f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
+  f.nlin = g.nlin; f.lin = const_cast<float4*>(part) + g.npart1;
   f.regime = g.regime; f.mode = FIN_THRESHOLD;
   f.p0 = lam;
   f.p1 = -fabsf(tanhf(lam));   // c0 of NQ:79 / NQ:105
@@ -261,6 +338,12 @@ int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const
 
 int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st) {
   FinJob f = make_fin(g, part, ds, s, lam);
+  if (g.nlin) {   // two-level second stage
+    if (g.C * g.nlin > 0x7fffffffll) { set_error("too many intermediate partials"); return LQ_E_BADSHAPE; }
+    int rc = launch_after(fold_partials_kernel, dim3((unsigned)(g.C * g.nlin)), dim3(256), st, "fold launch", f);
+    if (rc) return rc;
+    f.part = f.lin; f.regime = REG_LIN;
+  }
   return launch_after(finalize_kernel, dim3((unsigned)g.C), dim3(kFinThreads), st, "finalize launch", f);
 }
 

@@ -41,6 +41,13 @@ struct OpBase {
   static constexpr int kDeferSlots = 0;
   __device__ __forceinline__ PlainCtx prep(float s, const float4& aux) const { return PlainCtx{s, aux}; }
   __device__ __forceinline__ void flush(Acc&, Defer&) const {}
+  // COL traversal: element of the thread's k-th column (its own group context and accumulator)
+  template <class C>
+  __device__ __forceinline__ void elem_k(float p, float d, const C& c, const Job& j, Acc* acc, int k,
+                                         float& o, float& q, Defer&) const {
+    static_cast<const D*>(this)->elem(p, d, c, j, acc[k], o, q);
+  }
+  __device__ __forceinline__ void flush_k(Acc*, Defer&) const {}
   template <class C>
   __device__ __forceinline__ void quad(const float4& p, const float4& d, const C& c, const Job& j, Acc& acc,
                                        float4& o, float4& q, Defer&) const {
@@ -166,7 +173,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
 
 // ------------------------------------------------------------------------- COL regime
 template <class Op, bool STREAM, bool VEC>
-__device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op, Acc* smem) {
+__device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue) {
   constexpr int V = VEC ? 4 : 1;
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
@@ -190,49 +197,53 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   }
   float* out = Op::kOutIsY ? j.y : j.dX;
   const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
+  Defer df;
+  df.slot = queue + (t >> 5) * (Op::kDeferSlots * 32) + (t & 31);
+  df.n = 0;
 
-  if (active) {
-    const long long step = j.by;
-    for (long long r = r0 + ty; r < r1; r += 4 * step) {
-      float p[4][V], d[4][V];
+  // The row loop is block-uniform (every thread runs the same trips; rows past the end and
+  // idle threads are predicated off), so the warp is converged at flush_k.
+  const long long step = j.by;
+  for (long long rb = r0; rb < r1; rb += 4 * step) {
+    float p[4][V], d[4][V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long rr = r + u * step;
-        if (rr < r1) {
-          const long long e = rr * j.W + col0;
-          if constexpr (VEC) {
-            const float4 pv = ld4<STREAM>(reinterpret_cast<const float4*>(j.P + e));
-            p[u][0] = pv.x; p[u][1] = pv.y; p[u][2] = pv.z; p[u][3] = pv.w;
-            if (Op::kIn2) {
-              const float4 dv = ld4<STREAM>(reinterpret_cast<const float4*>(j.dy + e));
-              d[u][0] = dv.x; d[u][1] = dv.y; d[u][2] = dv.z; d[u][3] = dv.w;
-            }
-          } else {
-            p[u][0] = ld1<STREAM>(j.P + e);
-            if (Op::kIn2) d[u][0] = ld1<STREAM>(j.dy + e);
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = rb + ty + u * step;
+      if (active && rr < r1) {
+        const long long e = rr * j.W + col0;
+        if constexpr (VEC) {
+          const float4 pv = ld4<STREAM>(reinterpret_cast<const float4*>(j.P + e));
+          p[u][0] = pv.x; p[u][1] = pv.y; p[u][2] = pv.z; p[u][3] = pv.w;
+          if (Op::kIn2) {
+            const float4 dv = ld4<STREAM>(reinterpret_cast<const float4*>(j.dy + e));
+            d[u][0] = dv.x; d[u][1] = dv.y; d[u][2] = dv.z; d[u][3] = dv.w;
           }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long rr = r + u * step;
-        if (rr < r1) {
-          const long long e = rr * j.W + col0;
-          float o[V], c[V];
-#pragma unroll
-          for (int k = 0; k < V; ++k)
-            op.elem(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc[k], o[k], c[k]);
-          if (wr) {
-            if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(out + e), make_float4(o[0], o[1], o[2], o[3]));
-            else st1<STREAM>(out + e, o[0]);
-          }
-          if (Op::kCodes && j.codes) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
-          }
+        } else {
+          p[u][0] = ld1<STREAM>(j.P + e);
+          if (Op::kIn2) d[u][0] = ld1<STREAM>(j.dy + e);
         }
       }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = rb + ty + u * step;
+      if (active && rr < r1) {
+        const long long e = rr * j.W + col0;
+        float o[V], c[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          op.elem_k(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc, k, o[k], c[k], df);
+        if (wr) {
+          if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(out + e), make_float4(o[0], o[1], o[2], o[3]));
+          else st1<STREAM>(out + e, o[0]);
+        }
+        if (Op::kCodes && j.codes) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+        }
+      }
+    }
+    if (Op::kDeferSlots) op.flush_k(acc, df);
   }
 
   if (Op::kReduce) {
@@ -265,10 +276,9 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 }
 
 template <class Op, bool STREAM, bool VEC>
-__device__ __forceinline__ void run_job(const Job& j, unsigned blk, const Op& op, Acc* smem) {
-  // ROW and COL never share a block, so the defer queue and the COL tree use the same bytes
-  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op, reinterpret_cast<float2*>(smem));
-  else run_col<Op, STREAM, VEC>(j, blk, op, smem);
+__device__ __forceinline__ void run_job(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue) {
+  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op, queue);
+  else run_col<Op, STREAM, VEC>(j, blk, op, smem, queue);
 }
 
 // Single-tensor kernels: the Job travels in the kernel parameters.  One instantiation per
@@ -277,8 +287,7 @@ template <class Op>
 struct SmemPlan {
   static constexpr int kQueueEntries = Op::kDeferSlots ? Op::kDeferSlots * kThreads : 1;
   static constexpr int kColBytes = Op::kReduce ? 4 * kThreads * (int)sizeof(Acc) : 16;
-  static constexpr int kRowBytes = kQueueEntries * (int)sizeof(float2);
-  static constexpr int kMtBytes = kColBytes > kRowBytes ? kColBytes : kRowBytes;
+  static constexpr int kColEntries = Op::kReduce ? 4 * kThreads : 1;
 };
 
 template <class Op, bool STREAM, bool VEC>
@@ -288,15 +297,16 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const __grid_constant__ J
 }
 template <class Op, bool STREAM, bool VEC>
 __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ Job j, const Op op) {
-  __shared__ Acc smem[Op::kReduce ? 4 * kThreads : 1];
-  run_col<Op, STREAM, VEC>(j, blockIdx.x, op, smem);
+  __shared__ Acc smem[SmemPlan<Op>::kColEntries];
+  __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
+  run_col<Op, STREAM, VEC>(j, blockIdx.x, op, smem, queue);
 }
 
 // Multi-tensor kernel: block -> tensor by binary search over block_begin.
 template <class Op>
 __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
-  __shared__ __align__(16) unsigned char smem_raw[SmemPlan<Op>::kMtBytes];
-  Acc* smem = reinterpret_cast<Acc*>(smem_raw);
+  __shared__ Acc smem[SmemPlan<Op>::kColEntries];
+  __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -304,13 +314,17 @@ __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ Jo
   }
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
-  if (j.vec) run_job<Op, false, true>(j, blk, op, smem);
-  else run_job<Op, false, false>(j, blk, op, smem);
+  if (j.vec) run_job<Op, false, true>(j, blk, op, smem, queue);
+  else run_job<Op, false, false>(j, blk, op, smem, queue);
 }
 
 constexpr int kFinThreads = 128;
 
+__device__ __forceinline__ long long partials_per_group(const FinJob& f) {
+  return f.regime == REG_ROW ? f.outer * f.nseg : (f.regime == REG_COL ? f.nchunks * f.inner : f.nlin);
+}
 __device__ __forceinline__ long long partial_index(const FinJob& f, long long g, long long k) {
+  if (f.regime == REG_LIN) return g * f.nlin + k;
   if (f.regime == REG_ROW) {
     const long long o = k / f.nseg, sg = k - o * f.nseg;
     return (o * f.C + g) * f.nseg + sg;
