@@ -203,11 +203,15 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 
   // The row loop is block-uniform (every thread runs the same trips; rows past the end and
   // idle threads are predicated off), so the warp is converged at flush_k.
+  // Rows per trip: 4 for the light operators; 2 for two-input reducing operators (the threshold
+  // backward), whose per-thread state (4 columns x {scale, reciprocal, 3 accumulators}) would
+  // otherwise push the kernel past 64 registers and halve the resident warps -- ncu showed that
+  // variant latency-bound on dependent-issue stalls at 4 warps per scheduler.
+  constexpr int U = (Op::kIn2 && Op::kReduce) ? 2 : 4;
   const long long step = j.by;
-  for (long long rb = r0; rb < r1; rb += 4 * step) {
-    float p[4][V], d[4][V];
+  auto load = [&](long long rb, float (&p)[U][V], float (&d)[U][V]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long rr = rb + ty + u * step;
       if (active && rr < r1) {
         const long long e = rr * j.W + col0;
@@ -224,8 +228,10 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
         }
       }
     }
+  };
+  auto compute = [&](long long rb, float (&p)[U][V], float (&d)[U][V]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long rr = rb + ty + u * step;
       if (active && rr < r1) {
         const long long e = rr * j.W + col0;
@@ -244,6 +250,15 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
       }
     }
     if (Op::kDeferSlots) op.flush_k(acc, df);
+  };
+  {
+    const long long trip = U * step;
+    float pa[U][V], da[U][V];
+#pragma unroll 1
+    for (long long rb = r0; rb < r1; rb += trip) {
+      load(rb, pa, da);
+      compute(rb, pa, da);
+    }
   }
 
   if (Op::kReduce) {
