@@ -125,6 +125,28 @@ int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_threshold, in
                  int round_mode, float qmin, float qmax,
                  void* ws, size_t ws_bytes, lq_stream_t stream);
 
+/* the step after the hot path.  One launch updates every tensor in descs with
+ * Keras 2.11 Adam / SGD semantics (keras/optimizers/optimizer_experimental/{adam,sgd}.py, the
+ * optimizers experiment.py:763-771 and CIFAR-10/paper_implementation/experiment.py:130-141
+ * construct), folding in: g *= grad_scale * (grad_scale_dev ? *grad_scale_dev : 1);
+ * g += 2 * l2 * p (keras.regularizers.l2, IMAGENETTE/.../experiment.py:638); decoupled
+ * weight decay p -= p * weight_decay * lr; and MinValueConstraint p = max(p, min_value)
+ * (NQ:35-46; pass -INFINITY for unconstrained tensors).  m / v are the optimizer slots
+ * (v unused by SGD; m may be NULL for SGD with momentum 0).  step is 1-based. */
+typedef struct lq_opt_desc {
+  float* p;        /* parameter or learned scale, updated in place */
+  const float* g;  /* its gradient                                 */
+  float* m;        /* Adam m / SGD momentum buffer                 */
+  float* v;        /* Adam v                                       */
+  int64_t n;
+  float l2, min_value, weight_decay;
+  uint32_t reserved;
+} lq_opt_desc;
+int lq_opt_adam(const lq_opt_desc* descs, int n, float lr, float beta1, float beta2, float eps,
+                int64_t step, float grad_scale, const float* grad_scale_dev, lq_stream_t stream);
+int lq_opt_sgd(const lq_opt_desc* descs, int n, float lr, float momentum, int nesterov,
+               float grad_scale, const float* grad_scale_dev, lq_stream_t stream);
+
 /* Host-buffer entry point (the end-to-end path bench.py times): pinned or pageable HOST
  * arrays in, HOST arrays out; chunks are staged through the caller's device workspace
  * (>= lq_host_workspace_bytes) on internal streams, copies overlapped with the kernels.

@@ -14,6 +14,7 @@ Drop-in modules (same class / function names as the reference trees):
 """
 from . import _lib, ops  # noqa: F401  (loads liblq.so)
 from ._lib import LqError, version  # noqa: F401
+from . import regularizers  # noqa: F401
 from .initializers import Constant, RandomNormal  # noqa: F401
 
 __all__ = ["ops", "LqError", "version", "RandomNormal", "Constant"]

@@ -30,6 +30,13 @@ class TensorDesc(C.Structure):
                 ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class OptDesc(C.Structure):
+    """struct lq_opt_desc (include/lq.h)."""
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int64), ("l2", C.c_float), ("min_value", C.c_float), ("weight_decay", C.c_float),
+                ("reserved", C.c_uint32)]
+
+
 class LqError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
@@ -55,6 +62,8 @@ SIGNATURES = {
     "lq_mt_fq_bwd": (_I, [_DESCS, _I, _F, _I, _I, _F, _F, _P, _SZ, _P]),
     "lq_host_workspace_bytes": (_I, [_I64, _I64, _I64, C.POINTER(_SZ)]),
     "lq_host_fq_fwd_bwd": (_I, [_P, _P, _P, _F, _P, _P, _P, _I64, _I64, _I64, _P, _SZ]),
+    "lq_opt_adam": (_I, [C.POINTER(OptDesc), _I, _F, _F, _F, _F, _I64, _F, _P, _P]),
+    "lq_opt_sgd": (_I, [C.POINTER(OptDesc), _I, _F, _F, _I, _F, _P, _P]),
     "lq_debug_divcheck": (_I, [_P, _I64, C.c_uint32, _P, _P]),
     "lq_dp_unique_id": (_I, [_P]),
     "lq_dp_init": (_I, [_P, _I, _I, C.POINTER(_P)]),

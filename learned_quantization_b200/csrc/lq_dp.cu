@@ -16,7 +16,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
 enum { ncclFloat32 = 7 };
-enum { ncclSum = 0, ncclMax = 2 };
+enum { ncclSum = 0, ncclMax = 2, ncclAvg = 4 };
 
 struct NcclApi {
   void* handle = nullptr;
@@ -113,6 +113,11 @@ extern "C" int lq_dp_allreduce(lq_dp_t* dp, float* flat, int64_t n, float scale,
   if (n == 0) return LQ_OK;
   if (!flat) { set_error("lq_dp_allreduce: null buffer"); return LQ_E_NULLPTR; }
   cudaStream_t st = (cudaStream_t)stream;
+  // scale == 1/world is the data-parallel mean: NCCL's own average op does it inside the
+  // collective (one kernel, NVLS-capable); any other scale is a sum followed by one scaling pass.
+  const float mean = 1.0f / (float)dp->world;
+  if (scale == mean && dp->world > 1)
+    return nccl_fail(g_nccl.AllReduce(flat, flat, (size_t)n, ncclFloat32, ncclAvg, dp->comm, st), "ncclAllReduce(avg)");
   int rc = nccl_fail(g_nccl.AllReduce(flat, flat, (size_t)n, ncclFloat32, ncclSum, dp->comm, st), "ncclAllReduce");
   if (rc) return rc;
   if (scale != 1.0f) {

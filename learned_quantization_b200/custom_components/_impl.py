@@ -96,6 +96,7 @@ class QuantizedScaleLayerBase(nn.Module):
         self.orientation = orientation
         self.built = False
         self.constraint = MinValueConstraint(eps_float32 * 100)
+        self._banked = None        # set by training.step.QuantBank: pre-computed y for this step
 
     def _threshold(self) -> float:
         return 0.0
@@ -108,6 +109,10 @@ class QuantizedScaleLayerBase(nn.Module):
     def forward(self, inputs):
         if not self.built:
             self.build(tuple(inputs.shape), inputs.device)
+        if self._banked is not None:
+            # step-level multi-tensor path: y was produced by ONE lq_mt_fq_fwd launch over all
+            # layers; its gradient is consumed by ONE lq_mt_fq_bwd launch (training/step.py)
+            return self._banked
         return fake_quant(inputs, self.scale, self._threshold(), self._sgrad_mode)
 
     call = forward

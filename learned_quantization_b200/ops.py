@@ -248,3 +248,42 @@ def host_fq_fwd_bwd(hP: torch.Tensor, hs: torch.Tensor, hdy: torch.Tensor, penal
         check(lib.lq_host_fq_fwd_bwd(hP.data_ptr(), hs.data_ptr(), hdy.data_ptr(), float(penalty_threshold),
                                      hy.data_ptr(), None if hdX is None else hdX.data_ptr(), hds.data_ptr(),
                                      layout[0], layout[1], layout[2], dev_ws.data_ptr(), dev_ws.numel()))
+
+
+# --------------------------------------------------------------------- optimizer step
+class OptimizerTable:
+    """The descriptor table of one optimizer over a fixed set of tensors: built once (pointers of
+    parameters, gradients and slots are stable across steps), passed to lq_opt_* every step."""
+
+    def __init__(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], *, adam: bool,
+                 momentum: bool = True, l2: Optional[Sequence[float]] = None,
+                 min_value: Optional[Sequence[Optional[float]]] = None, weight_decay: float = 0.0):
+        _require_cuda(*params, *grads)
+        n = len(params)
+        l2 = list(l2) if l2 is not None else [0.0] * n
+        min_value = list(min_value) if min_value is not None else [None] * n
+        self.params, self.grads = list(params), list(grads)
+        self.m = [torch.zeros_like(p) for p in params] if (adam or momentum) else [None] * n
+        self.v = [torch.zeros_like(p) for p in params] if adam else [None] * n
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self.descs = (_lib.OptDesc * n)(*[
+            _lib.OptDesc(p=p.data_ptr(), g=g.data_ptr(), m=ptr(m), v=ptr(v), n=p.numel(), l2=float(l),
+                         min_value=(NEG_INF if mv is None else float(mv)), weight_decay=float(weight_decay), reserved=0)
+            for p, g, m, v, l, mv in zip(params, grads, self.m, self.v, l2, min_value)])
+        self.n = n
+        self.device = params[0].device if n else None
+
+
+def opt_adam(table: OptimizerTable, lr: float, step: int, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+             grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None) -> None:
+    """Keras-2.11 Adam over every tensor of the table, with l2 / weight decay / MinValueConstraint folded in."""
+    with torch.cuda.device(table.device):
+        check(lib.lq_opt_adam(table.descs, table.n, float(lr), float(beta_1), float(beta_2), float(epsilon), int(step),
+                              float(grad_scale), None if grad_scale_dev is None else grad_scale_dev.data_ptr(), _stream()))
+
+
+def opt_sgd(table: OptimizerTable, lr: float, momentum: float = 0.0, nesterov: bool = False,
+            grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None) -> None:
+    with torch.cuda.device(table.device):
+        check(lib.lq_opt_sgd(table.descs, table.n, float(lr), float(momentum), int(bool(nesterov)),
+                             float(grad_scale), None if grad_scale_dev is None else grad_scale_dev.data_ptr(), _stream()))

@@ -1,0 +1,139 @@
+"""Data parallelism for the QAT step: the batch is sharded, parameters are replicated, and once
+per step a flat fp32 bucket of gradients is mean-allreduced.
+
+Bucket layout (GradBucket):   [ dy of every quantised parameter | gradients of the plain
+parameters (BatchNorm, unquantised Dense) | ds of every learned scale ]
+
+The learned-scale gradient of the nested variant (NQ:62-118) is NOT linear in dy (threshold,
+group-wide AND, tanh), so "average the per-rank ds" differs from the reference evaluated on the
+global batch.  Two orders of operations are offered:
+
+    exact  allreduce [dy | plain] first; every rank then runs the threshold backward on the
+           AVERAGED dy: identical inputs on every rank => bit-identical ds, no ds traffic, and the
+           result equals the single-GPU reference on the concatenated batch (up to the
+           summation order of dy).  Default.
+    local  run the threshold backward on the local dy, then allreduce [dy | plain | ds]:
+           what BASELINE.json's wording describes ("learned-scale gradients are allreduced").
+
+`exchange_gradients` is that ordering and nothing else, so that it can be exercised with the
+gloo backend on CPU tensors (tests/test_dp_gloo.py); the product path plugs in NcclComm and the
+CUDA backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from .. import _lib
+from .._lib import check, lib
+
+
+class Comm:
+    world: int = 1
+    rank: int = 0
+
+    def allreduce_mean_(self, flat: torch.Tensor) -> None:
+        raise NotImplementedError
+
+
+class SingleComm(Comm):
+    def allreduce_mean_(self, flat):
+        return None
+
+
+class NcclComm(Comm):
+    """lq_dp_* (include/lq.h): our own NCCL communicator over NVLink 5 / NVSwitch, bootstrapped
+    by broadcasting the 128-byte unique id through an existing torch.distributed group (any backend)."""
+
+    def __init__(self, rank: Optional[int] = None, world: Optional[int] = None, id_bytes: Optional[bytes] = None):
+        import torch.distributed as dist
+        if rank is None:
+            rank, world = dist.get_rank(), dist.get_world_size()
+        self.rank, self.world = int(rank), int(world)
+        if id_bytes is None:
+            buf = C.create_string_buffer(128)
+            if self.rank == 0:
+                check(lib.lq_dp_unique_id(buf))
+            box = [bytes(buf.raw)]
+            dist.broadcast_object_list(box, src=0)
+            id_bytes = box[0]
+        self._h = C.c_void_p()
+        check(lib.lq_dp_init(id_bytes, self.rank, self.world, C.byref(self._h)))
+
+    def allreduce_mean_(self, flat: torch.Tensor) -> None:
+        if not flat.is_cuda or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("NcclComm.allreduce_mean_ takes a contiguous fp32 CUDA tensor")
+        if flat.numel() == 0:
+            return
+        check(lib.lq_dp_allreduce(self._h, flat.data_ptr(), flat.numel(), 1.0 / self.world,
+                                  torch.cuda.current_stream().cuda_stream))
+
+    def allreduce_max_(self, flat: torch.Tensor) -> None:
+        check(lib.lq_dp_allreduce_max(self._h, flat.data_ptr(), flat.numel(), torch.cuda.current_stream().cuda_stream))
+
+    def close(self):
+        if self._h:
+            check(lib.lq_dp_destroy(self._h))
+            self._h = C.c_void_p()
+
+
+class TorchDistComm(Comm):
+    """The same interface over a torch.distributed process group (gloo on CPU in the tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self._group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allreduce_mean_(self, flat):
+        if flat.numel() == 0:
+            return
+        self._dist.all_reduce(flat, op=self._dist.ReduceOp.SUM, group=self._group)
+        flat.mul_(1.0 / self.world)
+
+
+class GradBucket:
+    """One flat fp32 buffer with views for every gradient, in the order [dy | plain | ds]."""
+
+    def __init__(self, quant_shapes: Sequence[Sequence[int]], plain_shapes: Sequence[Sequence[int]],
+                 scale_shapes: Sequence[Sequence[int]], device, align: int = 4):
+        def carve(shapes, off):
+            spans = []
+            for shp in shapes:
+                n = 1
+                for d in shp:
+                    n *= int(d)
+                spans.append((off, n, tuple(int(d) for d in shp)))
+                off += -(-n // align) * align        # keep every view 16-byte aligned for the 128-bit paths
+            return spans, off
+        q, off = carve(quant_shapes, 0)
+        p, off = carve(plain_shapes, off)
+        self.n_exact = off                            # [dy | plain] is what EXACT mode exchanges
+        s, off = carve(scale_shapes, off)
+        self.n_total = off
+        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        view = lambda span: self.flat[span[0]:span[0] + span[1]].view(span[2])
+        self.dy = [view(x) for x in q]
+        self.plain = [view(x) for x in p]
+        self.ds = [view(x) for x in s]
+
+    def exact_part(self) -> torch.Tensor:
+        return self.flat[: self.n_exact]
+
+    def all(self) -> torch.Tensor:
+        return self.flat[: self.n_total]
+
+
+def exchange_gradients(bucket: GradBucket, comm: Comm, scale_backward: Callable[[], None], mode: str = "exact") -> None:
+    """Order the scale backward and the collective as `mode` says.  `scale_backward()` must read
+    bucket.dy and write bucket.ds (the threshold rule, or zeros for the STE variants)."""
+    if mode == "exact":
+        comm.allreduce_mean_(bucket.exact_part())
+        scale_backward()
+    elif mode == "local":
+        scale_backward()
+        comm.allreduce_mean_(bucket.all())
+    else:
+        raise ValueError(f"mode must be 'exact' or 'local', got {mode!r}")

@@ -1,0 +1,152 @@
+"""The QAT training step around the hot path, one launch per phase.
+
+Per step, for a model with T quantised tensors (T = 40 for the IMAGENETTE ResNet, 22 for
+paper_implementation, 4 for MNIST -- SURVEY Appendix C) the per-layer path of the drop-in layers
+launches T forward kernels and 2T backward kernels, plus Keras-style per-variable optimizer and
+constraint ops.  Here:
+
+    QuantBank.forward()      1 launch   lq_mt_fq_fwd over all (P, s)         NQ:55-60
+    model forward / loss / autograd backward  (cuDNN / cuBLAS through torch; not ours)
+    gather dy + plain grads  torch._foreach_copy_ into the flat GradBucket
+    exchange_gradients()     1 collective (lq_dp_allreduce) + QuantBank.backward():
+                             2 launches lq_mt_fq_bwd (+ second stage)        NQ:62-118
+    optimizer                1-3 launches lq_opt_adam / lq_opt_sgd with l2, 1/world scaling and
+                             MinValueConstraint folded in                    NQ:35-46, experiment.py:763-771
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+from torch import nn
+
+from .. import _lib, ops
+from ..custom_components import _impl
+from .dp import Comm, GradBucket, SingleComm, exchange_gradients
+
+
+def quantised_pairs(model: nn.Module):
+    """[(host layer, attribute name of the parameter, parameter, its CustomQuantizedScaleLayer)] in module order."""
+    out = []
+    for m in model.modules():
+        if isinstance(m, _impl.DenseLayerBase) and m.built:
+            out.append((m, "W", m.W, m.nested_q_w_layer))
+            out.append((m, "b", m.b, m.nested_q_b_layer))
+        elif isinstance(m, _impl.Conv2DLayerBase) and m.built:
+            out.append((m, "kernel", m.kernel, m.nested_q_k_layer))
+            if m._use_bias:
+                out.append((m, "b", m.b, m.nested_q_b_layer))
+    return out
+
+
+class QuantBank:
+    """Every quantised tensor of a (built) model, driven through the multi-tensor entry points."""
+
+    def __init__(self, model: nn.Module):
+        self.pairs = quantised_pairs(model)
+        if not self.pairs:
+            raise ValueError("model has no built quantised layers (run one forward first)")
+        self.hosts = [h for h, _, _, _ in self.pairs]
+        self.params = [p for _, _, p, _ in self.pairs]
+        self.qlayers = [q for _, _, _, q in self.pairs]
+        self.scales = [q.scale for q in self.qlayers]
+        self.layouts = [ops.group_layout(p.shape, s.shape) for p, s in zip(self.params, self.scales)]
+        modes = {q._sgrad_mode for q in self.qlayers}
+        lams = {float(q._threshold() or 0.0) for q in self.qlayers}
+        if len(modes) != 1 or len(lams) != 1:
+            raise ValueError("QuantBank needs one scale-gradient rule and one penalty threshold per model")
+        self.sgrad_mode, self.lam = modes.pop(), lams.pop()
+        dev = self.params[0].device
+        total = sum(-(-p.numel() // 4) * 4 for p in self.params)
+        self._yflat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.ys, off = [], 0
+        for p in self.params:
+            self.ys.append(self._yflat[off:off + p.numel()].view(p.shape).requires_grad_(True))
+            off += -(-p.numel() // 4) * 4
+
+    def forward(self) -> None:
+        """ONE launch: y_i = floor(P_i / s_i) * s_i for every tensor; layers then hand out y_i."""
+        with torch.no_grad():
+            ops.mt_fq_fwd([p.data for p in self.params], [s.data for s in self.scales],
+                          [y.data for y in self.ys], self.layouts)
+        for q, y in zip(self.qlayers, self.ys):
+            y.grad = None
+            q._banked = y
+
+    def release(self) -> None:
+        for q in self.qlayers:
+            q._banked = None
+
+    def backward(self, dys: List[torch.Tensor], dss: List[torch.Tensor]) -> None:
+        """dss_i <- scale gradient from dys_i (the parameter gradient is dys_i itself, NQ:118)."""
+        with torch.no_grad():
+            ops.mt_fq_bwd(dys, [p.data for p in self.params], [s.data for s in self.scales], dss,
+                          self.lam, self.layouts, scale_grad_mode=self.sgrad_mode)
+
+
+class TrainStep:
+    """forward -> loss -> backward -> gradient exchange -> fused optimizer, for a built model.
+
+    loss_fn(y_true, y_pred) returns per-sample losses (Keras convention; the step takes the mean).
+    optimizer: "adam" (Keras Adam: lr, 0.9, 0.999, 1e-7) or "sgd" (momentum / nesterov / weight_decay).
+    """
+
+    def __init__(self, model: nn.Module, loss_fn: Callable, *, optimizer: str = "adam", lr: float = 1e-4,
+                 momentum: float = 0.0, nesterov: bool = False, weight_decay: float = 0.0,
+                 comm: Optional[Comm] = None, ds_mode: str = "exact"):
+        self.model, self.loss_fn = model, loss_fn
+        self.comm = comm or SingleComm()
+        self.ds_mode = ds_mode
+        self.bank = QuantBank(model)
+        b = self.bank
+        quant_ids = {id(p) for p in b.params} | {id(s) for s in b.scales}
+        self.plain = [p for p in model.parameters() if id(p) not in quant_ids and p.requires_grad]
+        dev = b.params[0].device
+        self.bucket = GradBucket([p.shape for p in b.params], [p.shape for p in self.plain],
+                                 [s.shape for s in b.scales], dev)
+        # optimizer table over [P | plain | s], gradients = the bucket views (pointers never change)
+        l2 = []
+        for host in b.hosts:
+            reg = getattr(host, "regularizer", None)
+            l2.append(float(getattr(reg, "l2", 0.0)) if reg is not None else 0.0)
+        params = [p.data for p in b.params] + [p.data for p in self.plain] + [s.data for s in b.scales]
+        grads = self.bucket.dy + self.bucket.plain + self.bucket.ds
+        l2s = l2 + [0.0] * len(self.plain) + [0.0] * len(b.scales)
+        mins = [None] * (len(b.params) + len(self.plain)) + [float(q.constraint.min_value) for q in b.qlayers]
+        self.optimizer, self.lr = optimizer, lr
+        self.momentum, self.nesterov = momentum, nesterov
+        self.table = ops.OptimizerTable(params, grads, adam=(optimizer == "adam"), momentum=(momentum != 0.0),
+                                        l2=l2s, min_value=mins, weight_decay=weight_decay)
+        self.iterations = 0
+
+    def _scale_backward(self):
+        self.bank.backward(self.bucket.dy, self.bucket.ds)
+
+    def __call__(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+        b, bucket = self.bank, self.bucket
+        b.forward()
+        for p in self.plain:
+            p.grad = None
+        for t in b.params + b.scales:
+            t.grad = None
+        loss = self.loss_fn(y_true, self.model(x)).mean()
+        loss.backward()
+        with torch.no_grad():
+            torch._foreach_copy_(bucket.dy, [y.grad for y in b.ys])
+            if self.plain:
+                torch._foreach_copy_(bucket.plain, [p.grad for p in self.plain])
+            # loss terms that act on P / s directly (custom_loss_terms penalties): identical on every
+            # rank, so adding them before the mean-allreduce leaves them unchanged
+            extra_p = [(v, p.grad) for v, p in zip(bucket.dy, b.params) if p.grad is not None]
+            if extra_p:
+                torch._foreach_add_([v for v, _ in extra_p], [g for _, g in extra_p])
+            exchange_gradients(bucket, self.comm, self._scale_backward, self.ds_mode)
+            extra_s = [(v, s.grad) for v, s in zip(bucket.ds, b.scales) if s.grad is not None]
+            if extra_s:
+                torch._foreach_add_([v for v, _ in extra_s], [g.view(v.shape) for v, g in extra_s])
+            self.iterations += 1
+            if self.optimizer == "adam":
+                ops.opt_adam(self.table, self.lr, self.iterations)
+            else:
+                ops.opt_sgd(self.table, self.lr, self.momentum, self.nesterov)
+        return loss.detach()

@@ -335,3 +335,56 @@ def code_stats(P, s):
     """(number of unique codes, max|q|) as custom_callbacks.py:84-129 logs them."""
     q, _ = fq_forward(P, s)
     return int(np.unique(q).size), float(np.max(np.abs(q)))
+
+
+# ----------------------------------------------------------------------------------
+# f1  optimizer step + constraint (the step right after the hot path)
+#
+# PARITY STATUS of this block: UNPINNED.  The update rules live in Keras 2.11
+# (tensorflow==2.11.0, requirements.txt:1; keras/optimizers/optimizer_experimental/adam.py
+# and sgd.py, `update_step`), which is neither vendored in the reference nor installable
+# here; they are restated from the published source, one numpy fp32 op per TF op.  Call
+# sites: IMAGENETTE/nested_quantization_layer/experiment.py:763-771 (Adam(1e-4)),
+# CIFAR-10/paper_implementation/experiment.py:130-141 (SGD 0.1 / 0.9 / nesterov / wd 5e-4);
+# the constraint is NQ:35-46 applied after the update (Optimizer.apply_gradients).
+# ----------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, step, beta_1=0.9, beta_2=0.999, epsilon=1e-7, l2=0.0, min_value=None,
+              weight_decay=0.0, grad_scale=1.0):
+    """One Keras-2.11 Adam update; returns (p, m, v).  `l2` adds the keras.regularizers.l2
+    gradient 2*l2*p; `min_value` applies MinValueConstraint afterwards."""
+    p, g, m, v = (np.asarray(a, F32) for a in (p, g, m, v))
+    lr, b1, b2, eps = F32(lr), F32(beta_1), F32(beta_2), F32(epsilon)
+    g = g * F32(grad_scale)
+    if l2:
+        g = g + (F32(2.0) * F32(l2)) * p
+    if weight_decay:
+        p = p - p * F32(weight_decay) * lr
+    local_step = F32(step)
+    beta_1_power = np.power(b1, local_step, dtype=F32)
+    beta_2_power = np.power(b2, local_step, dtype=F32)
+    alpha = lr * np.sqrt(F32(1) - beta_2_power) / (F32(1) - beta_1_power)
+    m = m + (g - m) * (F32(1) - b1)
+    v = v + (np.square(g) - v) * (F32(1) - b2)
+    p = p - (m * alpha) / (np.sqrt(v) + eps)
+    if min_value is not None:
+        p = min_value_constraint(p, F32(min_value))
+    return p.astype(F32), m.astype(F32), v.astype(F32)
+
+
+def sgd_step(p, g, m, lr, momentum=0.0, nesterov=False, l2=0.0, min_value=None, weight_decay=0.0, grad_scale=1.0):
+    """One Keras-2.11 SGD update; returns (p, m)."""
+    p, g = np.asarray(p, F32), np.asarray(g, F32)
+    lr, mom = F32(lr), F32(momentum)
+    g = g * F32(grad_scale)
+    if l2:
+        g = g + (F32(2.0) * F32(l2)) * p
+    if weight_decay:
+        p = p - p * F32(weight_decay) * lr
+    if momentum:
+        m = -g * lr + np.asarray(m, F32) * mom
+        p = p + ((-g * lr + m * mom) if nesterov else m)
+    else:
+        p = p + (-g * lr)
+    if min_value is not None:
+        p = min_value_constraint(p, F32(min_value))
+    return p.astype(F32), (None if m is None else np.asarray(m, F32))

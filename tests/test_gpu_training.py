@@ -1,0 +1,190 @@
+"""GPU tier: the step after / around the hot path -- fused optimizer + constraint,
+the one-launch-per-phase QuantBank, the TrainStep, and the model builders' tensor inventories."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import lq_oracle as o
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lq():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    import learned_quantization_b200 as pkg
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return pkg
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+SIZES = [1, 3, 4, 5, 127, 4096, 4097, 10000, 70001]
+
+
+def _tensors(rng):
+    ps = [rng.normal(0, 0.05, n).astype(np.float32) for n in SIZES]
+    gs = [rng.normal(0, 1e-2, n).astype(np.float32) for n in SIZES]
+    l2 = [0.0 if i % 2 else 1e-4 for i in range(len(SIZES))]
+    mins = [None if i % 3 else 0.01 for i in range(len(SIZES))]
+    return ps, gs, l2, mins
+
+
+def test_fused_adam_matches_keras_restatement(lq):
+    ops = lq.ops
+    rng = np.random.default_rng(5)
+    ps, gs, l2, mins = _tensors(rng)
+    P, G = [dev(p) for p in ps], [dev(g) for g in gs]
+    table = ops.OptimizerTable(P, G, adam=True, l2=l2, min_value=mins, weight_decay=0.0)
+    ms, vs = [np.zeros_like(p) for p in ps], [np.zeros_like(p) for p in ps]
+    for step in (1, 2, 3):
+        scale_dev = torch.tensor(0.5, device="cuda")
+        ops.opt_adam(table, 1e-3, step, grad_scale=2.0, grad_scale_dev=scale_dev)      # net scale 1.0
+        for i in range(len(ps)):
+            ps[i], ms[i], vs[i] = o.adam_step(ps[i], gs[i], ms[i], vs[i], 1e-3, step, l2=l2[i], min_value=mins[i])
+            assert rel_err(P[i].cpu().numpy(), ps[i], tiny=1e-12) < 2e-6, (step, i)
+            assert rel_err(table.m[i].cpu().numpy(), ms[i], tiny=1e-12) < 2e-6
+            assert rel_err(table.v[i].cpu().numpy(), vs[i], tiny=1e-12) < 2e-6
+            if mins[i] is not None:
+                assert float(P[i].min()) >= float(np.float32(mins[i]))
+        for g, gh in zip(G, gs):                     # new gradients every step
+            gh[:] = rng.normal(0, 1e-2, gh.shape).astype(np.float32)
+            g.copy_(dev(gh))
+
+
+@pytest.mark.parametrize("momentum,nesterov,wd", [(0.0, False, 0.0), (0.9, False, 0.0), (0.9, True, 5e-4)])
+def test_fused_sgd_matches_keras_restatement(lq, momentum, nesterov, wd):
+    ops = lq.ops
+    rng = np.random.default_rng(6)
+    ps, gs, l2, mins = _tensors(rng)
+    P, G = [dev(p) for p in ps], [dev(g) for g in gs]
+    table = ops.OptimizerTable(P, G, adam=False, momentum=(momentum != 0.0), l2=l2, min_value=mins, weight_decay=wd)
+    ms = [np.zeros_like(p) for p in ps]
+    for _ in range(3):
+        ops.opt_sgd(table, 0.1, momentum, nesterov)
+        for i in range(len(ps)):
+            ps[i], m = o.sgd_step(ps[i], gs[i], ms[i], 0.1, momentum, nesterov, l2=l2[i], min_value=mins[i], weight_decay=wd)
+            if momentum:
+                ms[i] = m
+                assert rel_err(table.m[i].cpu().numpy(), ms[i], tiny=1e-12) < 2e-6
+            assert rel_err(P[i].cpu().numpy(), ps[i], tiny=1e-12) < 2e-6, i
+
+
+def test_optimizer_errors(lq):
+    from learned_quantization_b200 import _lib
+    d = (_lib.OptDesc * 1)(_lib.OptDesc(p=None, g=None, m=None, v=None, n=4, l2=0, min_value=0, weight_decay=0, reserved=0))
+    assert _lib.lib.lq_opt_adam(d, 1, 1e-3, 0.9, 0.999, 1e-7, 1, 1.0, None, None) == -1
+    assert _lib.lib.lq_opt_adam(d, 1, 1e-3, 0.9, 0.999, 1e-7, 0, 1.0, None, None) == -3
+
+
+class _TinyNet(torch.nn.Module):
+    def __init__(self, L, lam, orientation):
+        super().__init__()
+        from learned_quantization_b200 import RandomNormal, regularizers
+        init = RandomNormal(seed=3)
+        self.c1 = L.CustomConv2DLayer(seed=3, penalty_threshold=lam, orientation=orientation, initializer=init, filters=8,
+                                      kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
+                                      regularizer=regularizers.l2(1e-4))
+        self.c2 = L.CustomConv2DLayer(seed=3, penalty_threshold=lam, orientation=orientation, initializer=init, filters=16,
+                                      kernel_size=(3, 3), strides=(2, 2), padding="same", name="b", regularizer=None)
+        self.fc = L.CustomDenseLayer(seed=3, units=10, penalty_threshold=lam, orientation="columnwise", initializer=init,
+                                     name="fc", regularizer=None)
+        self.plain = torch.nn.Linear(10, 10)
+
+    def forward(self, x):
+        x = torch.relu(self.c1(x))
+        x = torch.relu(self.c2(x)).mean(dim=(1, 2))
+        return torch.softmax(self.plain(self.fc(x)), dim=-1)
+
+
+@pytest.mark.parametrize("orientation", ["channelwise", "scalar", "rowwise"])
+def test_train_step_equals_per_layer_path_plus_keras_adam(lq, orientation):
+    """Bank path (1 launch per phase) == per-layer autograd path (one launch per tensor): same y,
+    same dP, same ds; and the fused update equals the restated Keras Adam + l2 + constraint."""
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training.step import TrainStep, quantised_pairs
+    torch.manual_seed(0)
+    net = _TinyNet(nq, 1e-3, orientation).cuda()
+    x = torch.rand(4, 12, 12, 3, device="cuda") * 255.0
+    y = torch.randint(0, 10, (4,), device="cuda")
+    net(x)                                             # builds the layers
+    pairs = quantised_pairs(net)
+    assert len(pairs) == 6
+    with torch.no_grad():                              # "trained" scales so that codes are small
+        for _, _, p, q in pairs:
+            q.scale.uniform_(5e-3, 2e-2)
+    # per-layer path
+    for p in net.parameters():
+        p.grad = None
+    scce(y, net(x)).mean().backward()
+    ref = {id(p): p.grad.clone() for p in net.parameters()}
+    before = {id(p): p.detach().clone() for p in net.parameters()}
+    # bank path
+    step = TrainStep(net, scce, optimizer="adam", lr=1e-3)
+    step(x, y)
+    b = step.bucket
+    for v, p in zip(b.dy, step.bank.params):
+        assert rel_err(v.cpu().numpy(), ref[id(p)].cpu().numpy(), tiny=1e-12) < 1e-5
+    for v, s in zip(b.ds, step.bank.scales):
+        r = ref[id(s)].cpu().numpy()
+        assert np.max(np.abs(v.cpu().numpy() - r)) <= 1e-5 * max(np.max(np.abs(r)), 1e-30) + 1e-12
+    for v, p in zip(b.plain, step.plain):
+        assert rel_err(v.cpu().numpy(), ref[id(p)].cpu().numpy(), tiny=1e-12) < 1e-5
+    # update: Keras Adam step 1 on those gradients; l2 on c1's kernel AND bias; constraint on scales
+    l2_of = {id(net.c1.kernel): 1e-4, id(net.c1.b): 1e-4}
+    scale_ids = {id(s) for s in step.bank.scales}
+    grads = {id(p): v for v, p in zip(b.dy + b.plain + b.ds, step.bank.params + step.plain + step.bank.scales)}
+    for p in net.parameters():
+        g = grads[id(p)].cpu().numpy().reshape(-1)
+        p0 = before[id(p)].cpu().numpy().reshape(-1)
+        want, _, _ = o.adam_step(p0, g, np.zeros_like(p0), np.zeros_like(p0), 1e-3, 1, l2=l2_of.get(id(p), 0.0),
+                                 min_value=(o.SCALE_INIT if id(p) in scale_ids else None))
+        assert rel_err(p.detach().cpu().numpy().reshape(-1), want, tiny=1e-12) < 2e-6
+    # layers fall back to the per-layer path once the bank is released
+    step.bank.release()
+    assert all(q._banked is None for q in step.bank.qlayers)
+
+
+def test_mnist_step_trains_and_keeps_scales_above_floor(lq):
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.training.step import TrainStep
+    torch.manual_seed(1)
+    net = models.mnist_mlp(1e-10, seed=42, orientation="rowwise").cuda()
+    x, y = models.synthetic_batch(32, (28, 28, 1), "cuda")
+    x = x / 255.0
+    net(x)
+    step = TrainStep(net, scce, optimizer="adam", lr=1e-3)
+    losses = [float(step(x, y)) for _ in range(30)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    for s in step.bank.scales:
+        assert float(s.min()) >= float(o.SCALE_INIT)
+
+
+def test_model_builders_have_the_reference_tensor_inventory(lq):
+    """40 quantised tensors / 11 166 912 kernel elements (IMAGENETTE), 22 (paper)."""
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.training.step import quantised_pairs
+    net = models.imagenette_resnet(1e-11, orientation="channelwise").cuda().eval()
+    with torch.no_grad():
+        out = net(torch.rand(2, 64, 64, 3, device="cuda") * 255)
+    assert out.shape == (2, 10)
+    pairs = quantised_pairs(net)
+    kernels = [p for _, name, p, _ in pairs if name == "kernel"]
+    assert len(pairs) == 40 and len(kernels) == 20
+    assert sum(k.numel() for k in kernels) == 11_166_912
+    assert sum(p.numel() for _, name, p, _ in pairs if name == "b") == 4_800
+    assert sum(q.scale.numel() for _, name, _, q in pairs) == 3_843 + 20
+    net2 = models.cifar_resnet18(0.0, orientation="scalar").cuda().eval()
+    with torch.no_grad():
+        out2 = net2(torch.rand(2, 32, 32, 3, device="cuda") * 255)
+    assert out2.shape == (2, 10)
+    assert len(quantised_pairs(net2)) == 22
