@@ -299,9 +299,93 @@ def run_ours(args):
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+    qat = None
+    if not args.no_qat:
+        del sets, y, dX, hP, hdy, hy, hws
+        torch.cuda.empty_cache()
+        qat = run_qat(args, rank, world, local)
+    if rank == 0:
+        if qat is not None:
+            line["qat"] = qat
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- QAT training step
+def run_qat(args, rank, world, local):
+    """Second half of BASELINE.json's metric: QAT images/s on the IMAGENETTE ResNet-style model
+    (20 quantised convs + biases = 40 quantised tensors, nested variant, channelwise scales,
+    lambda 1e-11, Adam 1e-4, 224x224x3, per-GPU batch 64 = the reference's batch), synthetic data.
+    Data parallel: batch sharded, [dy | plain grads] mean-allreduced through lq_dp_allreduce
+    (our NCCL communicator), scale gradients in EXACT mode (training/dp.py).  Weak scaling."""
+    import torch
+    import torch.distributed as dist
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.training.dp import NcclComm
+    from learned_quantization_b200.training.step import TrainStep
+
+    torch.backends.cudnn.allow_tf32 = True           # TF 2.11 enables TF32 convolutions by default too
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    batch, shape = args.qat_batch, (224, 224, 3)
+    torch.manual_seed(42)
+    net = models.imagenette_resnet(1e-11, seed=42, orientation="channelwise", variant="nested").cuda().train()
+    x, y = models.synthetic_batch(batch, shape, "cuda", seed=42 + rank)
+    with torch.no_grad():
+        net(x[:2])                                    # builds the layers
+    comm = NcclComm() if world > 1 else None
+    step = TrainStep(net, scce, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
+    hx = x.cpu().pin_memory()
+    hy = y.cpu().pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps, warm = args.qat_steps, max(3, args.qat_warmup)
+    for _ in range(warm):
+        step(x, y)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(x, y)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / steps
+    # end to end: batch from pinned host memory every step, loss read back every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step(hx.cuda(non_blocking=True), hy.cuda(non_blocking=True))
+        loss_host = float(loss)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    n_q = sum(p.numel() for p in step.bank.params)
+    out = {"metric": "qat_images_per_s", "value": batch * world / (dev_ms * 1e-3), "unit": "images/s",
+           "ms_per_step": dev_ms, "steps": steps, "warmup": warm,
+           "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
+           "config": {"workload": "imagenette_resnet_nested_channelwise_224", "per_gpu_batch": batch, "global_batch": batch * world,
+                      "optimizer": "adam(1e-4) fused with l2 + MinValueConstraint", "lambda": 1e-11,
+                      "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
+                      "scale_grad_mode": "exact (allreduce dy, then threshold backward on every rank)",
+                      "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}"},
+           "allreduce_floats": step.bucket.n_exact,
+           "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 2, "lq_opt_adam": -(-len(step.table.params) // 56),
+                                     "lq_dp_allreduce": 1 if world > 1 else 0},
+           "last_loss": loss_host}
+    if comm is not None:
+        comm.close()
+    return out
 
 
 # ------------------------------------------------------------------------- layout sweep
@@ -380,6 +464,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-qat", action="store_true", help="skip the QAT images/s section of the line")
+    ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
+    ap.add_argument("--qat-steps", type=int, default=20)
+    ap.add_argument("--qat-warmup", type=int, default=5)
     ap.add_argument("--sweep", action="store_true", help="layout/size sweep (one JSON line each) instead of the headline")
     ap.add_argument("--max-elems", type=int, default=1 << 28)
     ap.add_argument("--only", default="", help="comma-separated layout names for --sweep")
