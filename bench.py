@@ -347,13 +347,20 @@ def run_qat(args, rank, world, local):
         torch.cuda.synchronize()
 
     steps, warm = args.qat_steps, max(3, args.qat_warmup)
-    for _ in range(warm):
-        step(x, y)
+    if args.qat_eager:
+        run = step
+        for _ in range(warm):
+            step(x, y)
+    else:
+        step.capture(x, y, warmup=warm)               # whole step in one CUDA graph
+        run = step.replay
+        for _ in range(3):
+            run(x, y)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        step(x, y)
+        run(x, y)
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1) / steps
@@ -361,7 +368,7 @@ def run_qat(args, rank, world, local):
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        loss = step(hx.cuda(non_blocking=True), hy.cuda(non_blocking=True))
+        loss = run(hx, hy) if not args.qat_eager else step(hx.cuda(non_blocking=True), hy.cuda(non_blocking=True))
         loss_host = float(loss)
     barrier()
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
@@ -378,7 +385,8 @@ def run_qat(args, rank, world, local):
                       "optimizer": "adam(1e-4) fused with l2 + MinValueConstraint", "lambda": 1e-11,
                       "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
                       "scale_grad_mode": "exact (allreduce dy, then threshold backward on every rank)",
-                      "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}"},
+                      "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}",
+                      "launch": "eager" if args.qat_eager else "one CUDA graph per step"},
            "allreduce_floats": step.bucket.n_exact,
            "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 2, "lq_opt_adam": -(-len(step.table.params) // 56),
                                      "lq_dp_allreduce": 1 if world > 1 else 0},
@@ -468,6 +476,7 @@ def main():
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)
+    ap.add_argument("--qat-eager", action="store_true", help="do not capture the QAT step in a CUDA graph")
     ap.add_argument("--sweep", action="store_true", help="layout/size sweep (one JSON line each) instead of the headline")
     ap.add_argument("--max-elems", type=int, default=1 << 28)
     ap.add_argument("--only", default="", help="comma-separated layout names for --sweep")

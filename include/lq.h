@@ -132,7 +132,9 @@ int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_threshold, in
  * g += 2 * l2 * p (keras.regularizers.l2, IMAGENETTE/.../experiment.py:638); decoupled
  * weight decay p -= p * weight_decay * lr; and MinValueConstraint p = max(p, min_value)
  * (NQ:35-46; pass -INFINITY for unconstrained tensors).  m / v are the optimizer slots
- * (v unused by SGD; m may be NULL for SGD with momentum 0).  step is 1-based. */
+ * (v unused by SGD; m may be NULL for SGD with momentum 0).  step is 1-based; when step_dev
+ * (a device int64) is given it is read instead, so that a CUDA-graph replay of the step sees
+ * the current iteration. */
 typedef struct lq_opt_desc {
   float* p;        /* parameter or learned scale, updated in place */
   const float* g;  /* its gradient                                 */
@@ -143,7 +145,8 @@ typedef struct lq_opt_desc {
   uint32_t reserved;
 } lq_opt_desc;
 int lq_opt_adam(const lq_opt_desc* descs, int n, float lr, float beta1, float beta2, float eps,
-                int64_t step, float grad_scale, const float* grad_scale_dev, lq_stream_t stream);
+                int64_t step, const int64_t* step_dev, float grad_scale, const float* grad_scale_dev,
+                lq_stream_t stream);
 int lq_opt_sgd(const lq_opt_desc* descs, int n, float lr, float momentum, int nesterov,
                float grad_scale, const float* grad_scale_dev, lq_stream_t stream);
 

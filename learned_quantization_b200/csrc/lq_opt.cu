@@ -57,9 +57,22 @@ __device__ __forceinline__ float opt_one(float p, float g, float& m, float& v, c
   return fmaxf(p, j.min_value);      // -inf: no constraint
 }
 
+// Same expression as the host side of lq_opt_adam (fp32 pow / sqrt like tf.pow / tf.sqrt).
+__host__ __device__ inline float adam_alpha(float lr, float b1, float b2, float t) {
+  return lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+}
+
 template <bool ADAM>
-__global__ void __launch_bounds__(256) opt_kernel(const __grid_constant__ OptTable tab, const AdamArgs a, const SgdArgs s,
-                                                  float gscale, const float* gscale_dev) {
+__global__ void __launch_bounds__(256) opt_kernel(const __grid_constant__ OptTable tab, AdamArgs a, const SgdArgs s,
+                                                  float gscale, const float* gscale_dev, const long long* step_dev) {
+  if (ADAM && step_dev) {
+    // step counter in device memory (CUDA-graph replays cannot change a host scalar): one thread
+    // derives the bias-corrected step size for the block
+    __shared__ float alpha_s;
+    if (threadIdx.x == 0) alpha_s = adam_alpha(a.lr, a.b1, a.b2, (float)__ldg(step_dev));
+    __syncthreads();
+    a.alpha = alpha_s;
+  }
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(256) opt_kernel(const __grid_constant__ OptTab
 
 template <bool ADAM>
 static int opt_launch(const char* who, const lq_opt_desc* descs, int n, const AdamArgs& a, const SgdArgs& s,
-                      float gscale, const float* gscale_dev, cudaStream_t st) {
+                      float gscale, const float* gscale_dev, const long long* step_dev, cudaStream_t st) {
   if (n < 0) { set_error("%s: n < 0", who); return LQ_E_BADSHAPE; }
   if (n && !descs) { set_error("%s: null descs", who); return LQ_E_NULLPTR; }
   for (int i0 = 0; i0 < n; i0 += kOptMax) {
@@ -126,7 +139,7 @@ static int opt_launch(const char* who, const lq_opt_desc* descs, int n, const Ad
       total += (unsigned)blocks;
     }
     if (!total) continue;
-    opt_kernel<ADAM><<<dim3(total), dim3(256), 0, st>>>(tab, a, s, gscale, gscale_dev);
+    opt_kernel<ADAM><<<dim3(total), dim3(256), 0, st>>>(tab, a, s, gscale, gscale_dev, step_dev);
     int rc = cuda_fail(cudaGetLastError(), who);
     if (rc) return rc;
   }
@@ -138,17 +151,18 @@ static int opt_launch(const char* who, const lq_opt_desc* descs, int n, const Ad
 using namespace lq;
 
 extern "C" int lq_opt_adam(const lq_opt_desc* descs, int n, float lr, float beta1, float beta2, float eps,
-                           int64_t step, float grad_scale, const float* grad_scale_dev, lq_stream_t stream) {
-  if (step < 1) { set_error("lq_opt_adam: step is 1-based, got %lld", (long long)step); return LQ_E_BADMODE; }
+                           int64_t step, const int64_t* step_dev, float grad_scale, const float* grad_scale_dev,
+                           lq_stream_t stream) {
+  if (!step_dev && step < 1) { set_error("lq_opt_adam: step is 1-based, got %lld", (long long)step); return LQ_E_BADMODE; }
   AdamArgs a{lr, beta1, beta2, eps, 0.f};
   // alpha = lr * sqrt(1 - b2^t) / (1 - b1^t), in fp32 like tf.pow / tf.sqrt on fp32 variables
-  const float b1p = powf(beta1, (float)step), b2p = powf(beta2, (float)step);
-  a.alpha = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
-  return opt_launch<true>("lq_opt_adam", descs, n, a, SgdArgs{}, grad_scale, grad_scale_dev, (cudaStream_t)stream);
+  if (!step_dev) a.alpha = adam_alpha(lr, beta1, beta2, (float)step);
+  return opt_launch<true>("lq_opt_adam", descs, n, a, SgdArgs{}, grad_scale, grad_scale_dev,
+                          reinterpret_cast<const long long*>(step_dev), (cudaStream_t)stream);
 }
 
 extern "C" int lq_opt_sgd(const lq_opt_desc* descs, int n, float lr, float momentum, int nesterov,
                           float grad_scale, const float* grad_scale_dev, lq_stream_t stream) {
   SgdArgs s{lr, momentum, nesterov ? 1 : 0};
-  return opt_launch<false>("lq_opt_sgd", descs, n, AdamArgs{}, s, grad_scale, grad_scale_dev, (cudaStream_t)stream);
+  return opt_launch<false>("lq_opt_sgd", descs, n, AdamArgs{}, s, grad_scale, grad_scale_dev, nullptr, (cudaStream_t)stream);
 }

@@ -124,8 +124,11 @@ def _same_pad(n: int, k: int, s: int) -> Tuple[int, int]:
     return total // 2, total - total // 2
 
 
-def conv2d_nhwc(inputs, kernel_hwio, strides, padding: str):
-    """tf.nn.conv2d semantics (NHWC activations, HWIO filters, TF 'SAME' padding) on cuDNN."""
+def conv2d_nhwc(inputs, kernel_hwio, strides, padding: str, bias=None):
+    """tf.nn.conv2d semantics (NHWC activations, HWIO filters, TF 'SAME' padding) on cuDNN.
+    `bias` is added in the convolution's epilogue: the same single fp32 add per
+    output as NQ:350's tf.add(conv_output, qb), without the extra pass over the activation
+    and with the bias gradient produced by cuDNN's backward instead of a separate reduction."""
     if isinstance(strides, int):
         strides = (strides, strides)
     sh, sw = int(strides[0]), int(strides[1])
@@ -135,11 +138,11 @@ def conv2d_nhwc(inputs, kernel_hwio, strides, padding: str):
         pt, pb = _same_pad(x.shape[2], w.shape[2], sh)
         pl, pr = _same_pad(x.shape[3], w.shape[3], sw)
         if pt == pb and pl == pr:
-            y = F.conv2d(x, w, stride=(sh, sw), padding=(pt, pl))
+            y = F.conv2d(x, w, bias, stride=(sh, sw), padding=(pt, pl))
         else:
-            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, stride=(sh, sw))
+            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, bias, stride=(sh, sw))
     elif padding.upper() == "VALID":
-        y = F.conv2d(x, w, stride=(sh, sw))
+        y = F.conv2d(x, w, bias, stride=(sh, sw))
     else:
         raise ValueError(f"padding must be 'same' or 'valid', got {padding!r}")
     return y.permute(0, 2, 3, 1)
@@ -243,11 +246,10 @@ class Conv2DLayerBase(_HostLayer):
         if not self.built:
             self.build(tuple(inputs.shape), inputs.device)
         qk = self.nested_q_k_layer(self.kernel)                          # NQ:340
-        conv_output = conv2d_nhwc(inputs, qk, self.strides, self.padding)  # NQ:343-348
         if not self._use_bias:
-            return conv_output                                           # PI:365
+            return conv2d_nhwc(inputs, qk, self.strides, self.padding)   # PI:356-365
         qb = self.nested_q_b_layer(self.b)                               # NQ:341
-        return torch.add(conv_output, qb)                                # NQ:350
+        return conv2d_nhwc(inputs, qk, self.strides, self.padding, bias=qb)  # NQ:343-350 (add fused)
 
     call = forward
 

@@ -274,12 +274,20 @@ class OptimizerTable:
         self.device = params[0].device if n else None
 
 
-def opt_adam(table: OptimizerTable, lr: float, step: int, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+def opt_adam(table: OptimizerTable, lr: float, step, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
              grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None) -> None:
-    """Keras-2.11 Adam over every tensor of the table, with l2 / weight decay / MinValueConstraint folded in."""
+    """Keras-2.11 Adam over every tensor of the table, with l2 / weight decay / MinValueConstraint
+    folded in.  `step` is the 1-based iteration: a Python int, or a CUDA int64 tensor that the
+    kernel reads (for CUDA-graph replays)."""
+    step_dev = None
+    if isinstance(step, torch.Tensor):
+        if not step.is_cuda or step.dtype != torch.int64 or step.numel() != 1:
+            raise TypeError("a device step counter must be a CUDA int64 scalar tensor")
+        step_dev, step = step.data_ptr(), 0
     with torch.cuda.device(table.device):
         check(lib.lq_opt_adam(table.descs, table.n, float(lr), float(beta_1), float(beta_2), float(epsilon), int(step),
-                              float(grad_scale), None if grad_scale_dev is None else grad_scale_dev.data_ptr(), _stream()))
+                              step_dev, float(grad_scale),
+                              None if grad_scale_dev is None else grad_scale_dev.data_ptr(), _stream()))
 
 
 def opt_sgd(table: OptimizerTable, lr: float, momentum: float = 0.0, nesterov: bool = False,

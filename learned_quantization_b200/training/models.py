@@ -55,6 +55,12 @@ def _same_pool(x, k, s):
     ph = max((-(-h // s) - 1) * s + k - h, 0)
     pw = max((-(-w // s) - 1) * s + k - w, 0)
     xc = x.permute(0, 3, 1, 2)
+    if ph // 2 == 0 and pw // 2 == 0:
+        # all of TF's SAME padding falls on the bottom/right: windows clipped at the border
+        # (ceil_mode) are the same thing as -inf padding there, without materialising it
+        return F.max_pool2d(xc, k, s, ceil_mode=True).permute(0, 2, 3, 1)
+    if ph % 2 == 0 and pw % 2 == 0:
+        return F.max_pool2d(xc, k, s, padding=(ph // 2, pw // 2)).permute(0, 2, 3, 1)
     xc = F.pad(xc, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), value=float("-inf"))
     return F.max_pool2d(xc, k, s).permute(0, 2, 3, 1)
 

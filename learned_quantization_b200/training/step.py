@@ -118,6 +118,8 @@ class TrainStep:
         self.table = ops.OptimizerTable(params, grads, adam=(optimizer == "adam"), momentum=(momentum != 0.0),
                                         l2=l2s, min_value=mins, weight_decay=weight_decay)
         self.iterations = 0
+        self._step_dev = torch.zeros((), dtype=torch.int64, device=dev)   # Adam's t, read by the kernel
+        self._graph = None
 
     def _scale_backward(self):
         self.bank.backward(self.bucket.dy, self.bucket.ds)
@@ -145,8 +147,39 @@ class TrainStep:
             if extra_s:
                 torch._foreach_add_([v for v, _ in extra_s], [g.view(v.shape) for v, g in extra_s])
             self.iterations += 1
+            self._step_dev.add_(1)
             if self.optimizer == "adam":
-                ops.opt_adam(self.table, self.lr, self.iterations)
+                ops.opt_adam(self.table, self.lr, self._step_dev)
             else:
                 ops.opt_sgd(self.table, self.lr, self.momentum, self.nesterov)
         return loss.detach()
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, x: torch.Tensor, y_true: torch.Tensor, warmup: int = 3) -> None:
+        """Capture the whole step (forward, autograd backward, gradient exchange, fused optimizer) in
+        ONE CUDA graph: the step issues several hundred small launches (cuDNN, BatchNorm, our
+        multi-tensor kernels, NCCL) and is otherwise bounded by the host's launch rate.  Everything
+        the step changes between iterations lives in device memory (Adam's t included), so a replay
+        is exact.  `x`, `y_true` fix the static input shapes; replay() copies new batches into them."""
+        self._sx, self._sy = x.clone(), y_true.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                  # cuDNN autotuning and lazy allocations happen here
+                self(self._sx, self._sy)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._sloss = self(self._sx, self._sy)
+        self._graph = g
+
+    def replay(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+        """One captured step on a new batch (device or pinned-host tensors of the captured shapes)."""
+        if self._graph is None:
+            raise RuntimeError("call capture() first")
+        self._sx.copy_(x, non_blocking=True)
+        self._sy.copy_(y_true, non_blocking=True)
+        self._graph.replay()
+        self.iterations += 1
+        return self._sloss
