@@ -438,25 +438,45 @@ def run_sweep(args):
                          dtype=torch.uint8, device="cuda")
 
         def fwd(i):
-            check(lib.lq_fq_fwd(Ps[i].data_ptr(), s.data_ptr(), outs[i].data_ptr(), None, 0, *layout, 0, ninf, pinf, stream))
+            check(lib.lq_fq_fwd(Ps[i].data_ptr(), s.data_ptr(), outs[i].data_ptr(), None, 0, *layout, 0, ninf, pinf,
+                                torch.cuda.current_stream().cuda_stream))
 
         def bwd(i):
             check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), LAMBDA, outs[i].data_ptr(),
-                                          ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+                                          ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(),
+                                          torch.cuda.current_stream().cuda_stream))
 
         res = {}
+        graphed = n <= (1 << 24)      # launch-bound sizes: time a CUDA graph of `steps` launches
         for tag, fn in (("fwd", fwd), ("bwd", bwd)):
             for i in range(max(args.warmup, 3)):
                 fn(i % nsets)
             torch.cuda.synchronize()
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for i, (a, b) in enumerate(evs):
-                a.record(); fn(i % nsets); b.record()
-            torch.cuda.synchronize()
-            ts = sorted(a.elapsed_time(b) for a, b in evs)
-            res[tag] = ts[len(ts) // 2]
+            if graphed:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(args.steps):
+                        fn(i % nsets)
+                g.replay()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); g.replay(); b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) / args.steps)
+                res[tag] = sorted(ts)[len(ts) // 2]
+                del g
+            else:
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                for i, (a, b) in enumerate(evs):
+                    a.record(); fn(i % nsets); b.record()
+                torch.cuda.synchronize()
+                ts = sorted(a.elapsed_time(b) for a, b in evs)
+                res[tag] = ts[len(ts) // 2]
         gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
         print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "rotating_sets": nsets,
+                          "timing": f"CUDA graph of {args.steps} launches" if graphed else "per-launch CUDA events",
                           "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
                           "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),
                           "fwd_bwd_GBps": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9,

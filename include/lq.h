@@ -150,6 +150,22 @@ int lq_opt_adam(const lq_opt_desc* descs, int n, float lr, float beta1, float be
 int lq_opt_sgd(const lq_opt_desc* descs, int n, float lr, float momentum, int nesterov,
                float grad_scale, const float* grad_scale_dev, lq_stream_t stream);
 
+/* integer-code statistics on the device, replacing the per-epoch host round trip of
+ * custom_callbacks.py:84-129 (floor(kernel / scale) -> np.unique(return_counts=True), max|q|) and
+ * the unchecked .astype(np.int8) of utils/log_scripts.py:74-79.
+ * lq_code_range: out_min_max[0..1] (device) = smallest / largest code (NaN, NaN for an empty or
+ *   all-NaN tensor); ws: 8 bytes of device scratch.
+ * lq_code_histogram: hist[b] += #elements with code == code_lo + b (hist and *outside are device
+ *   buffers the CALLER zeroes; codes outside the window and NaNs are counted in *outside).
+ *   np.unique's values/counts are the non-zero bins; the int8 saturation count is the mass
+ *   outside [-128, 127]. */
+int lq_code_range(const float* P, const float* s, int64_t outer, int64_t C, int64_t inner,
+                  int round_mode, float qmin, float qmax, float* out_min_max,
+                  void* ws, size_t ws_bytes, lq_stream_t stream);
+int lq_code_histogram(const float* P, const float* s, int64_t outer, int64_t C, int64_t inner,
+                      int round_mode, float qmin, float qmax, int64_t code_lo, int64_t nbins,
+                      uint32_t* hist, unsigned long long* outside, lq_stream_t stream);
+
 /* Host-buffer entry point (the end-to-end path bench.py times): pinned or pageable HOST
  * arrays in, HOST arrays out; chunks are staged through the caller's device workspace
  * (>= lq_host_workspace_bytes) on internal streams, copies overlapped with the kernels.

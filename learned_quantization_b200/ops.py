@@ -295,3 +295,48 @@ def opt_sgd(table: OptimizerTable, lr: float, momentum: float = 0.0, nesterov: b
     with torch.cuda.device(table.device):
         check(lib.lq_opt_sgd(table.descs, table.n, float(lr), float(momentum), int(bool(nesterov)),
                              float(grad_scale), None if grad_scale_dev is None else grad_scale_dev.data_ptr(), _stream()))
+
+
+# --------------------------------------------------------------------- integer-code statistics
+def code_stats(P: torch.Tensor, s: torch.Tensor, layout=None, *, max_bins: int = 1 << 24,
+               round_mode: int = _lib.LQ_ROUND_FLOOR, qmin: float = NEG_INF, qmax: float = POS_INF) -> dict:
+    """What custom_callbacks.py:84-129 recomputes on the host every epoch, computed on the device:
+    np.unique(floor(P / s), return_counts=True), max |q|, and the number of codes that do not fit
+    int8 (utils/log_scripts.py:74-79 casts with .astype(np.int8), which wraps silently).
+    Two passes over P (range, then histogram); only the non-empty bins come back to the host."""
+    _require_cuda(P, s)
+    layout = layout or group_layout(P.shape, s.shape)
+    dev = P.device
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = workspace(256, dev, "codes")
+    with torch.cuda.device(dev):
+        check(lib.lq_code_range(P.data_ptr(), s.data_ptr(), *layout, round_mode, qmin, qmax, mm.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream()))
+    lo_f, hi_f = (float(v) for v in mm.cpu())
+    n = P.numel()
+    if n == 0 or math.isnan(lo_f):
+        return {"unique": torch.empty(0), "counts": torch.empty(0, dtype=torch.int64), "n_unique": 0,
+                "min": math.nan, "max": math.nan, "max_abs": math.nan, "outside_window": n, "int8_overflow": 0}
+    lim = float(1 << 30) - 1
+    lo = int(max(min(lo_f, lim), -lim))
+    hi = int(max(min(hi_f, lim), -lim))
+    nbins = min(hi - lo + 1, max_bins)
+    hist = torch.zeros(nbins, dtype=torch.int32, device=dev)
+    outside = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.lq_code_histogram(P.data_ptr(), s.data_ptr(), *layout, round_mode, qmin, qmax, lo, nbins,
+                                    hist.data_ptr(), outside.data_ptr(), _stream()))
+    nz = torch.nonzero(hist, as_tuple=False).flatten()
+    counts = hist[nz].to(torch.int64)
+    values = (nz + lo).to(torch.float32)
+    in8 = (values >= -128) & (values <= 127)
+    n_out = int(outside)
+    return {"unique": values.cpu(), "counts": counts.cpu(), "n_unique": int(nz.numel()), "min": lo_f, "max": hi_f,
+            "max_abs": max(abs(lo_f), abs(hi_f)), "outside_window": n_out,
+            "int8_overflow": int(counts[~in8].sum()) + n_out}
+
+
+def codes_int8(P: torch.Tensor, s: torch.Tensor, layout=None) -> torch.Tensor:
+    """floor(P / s).astype(int8) with numpy's wrap-around (utils/log_scripts.py:74-79), on the device."""
+    _, codes = fq_fwd(P, s, layout, codes_dtype=torch.int8)
+    return codes

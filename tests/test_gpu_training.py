@@ -220,3 +220,50 @@ def test_model_builders_have_the_reference_tensor_inventory(lq):
         out2 = net2(torch.rand(2, 32, 32, 3, device="cuda") * 255)
     assert out2.shape == (2, 10)
     assert len(quantised_pairs(net2)) == 22
+
+
+# ------------------------------------------------------------------ f2: code statistics / int8 export
+@pytest.mark.parametrize("shape,s_shape,s_range", [((3, 3, 16, 32), (1, 1, 16, 1), (5e-3, 2e-2)), ((784, 128), (784, 1), (5e-3, 2e-2)),
+                                                   ((5000,), (1,), (1.2e-5, 1.2e-5)), ((2, 3, 10001), (1, 3, 1), (1e-3, 1e-2))])
+def test_code_stats_equal_numpy_unique(lq, shape, s_shape, s_range):
+    """custom_callbacks.py:84-129: np.unique(floor(P / s), return_counts=True) and max|q|."""
+    ops = lq.ops
+    rng = np.random.default_rng(11)
+    P = rng.normal(0, 0.05, shape).astype(np.float32)
+    s = rng.uniform(*s_range, s_shape).astype(np.float32)
+    q = np.floor(P / s)
+    vals, cnts = np.unique(q.reshape(-1), return_counts=True)
+    st = ops.code_stats(dev(P), dev(s))
+    assert st["n_unique"] == len(vals) and st["outside_window"] == 0
+    assert np.array_equal(st["unique"].numpy(), vals.astype(np.float32)) and np.array_equal(st["counts"].numpy(), cnts)
+    assert st["min"] == vals[0] and st["max"] == vals[-1] and st["max_abs"] == np.max(np.abs(q))
+    assert st["int8_overflow"] == int(np.sum((q < -128) | (q > 127)))
+    # a window smaller than the range: the rest is counted, not dropped
+    st2 = ops.code_stats(dev(P), dev(s), max_bins=8)
+    assert st2["outside_window"] == int(np.sum(q >= vals[0] + 8)) and int(st2["counts"].sum()) + st2["outside_window"] == q.size
+    assert np.array_equal(ops.codes_int8(dev(P), dev(s)).cpu().numpy(), q.astype(np.int64).astype(np.int8))
+
+
+def test_save_compress_parameters_writes_the_reference_artefacts(lq, tmp_path):
+    """utils/log_scripts.py:61-97: weights.npy (dict of int8 codes), weights.zip, file_sizes.log."""
+    import zipfile
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.utils import log_scripts
+    net = models.mnist_mlp(1e-10, orientation="rowwise").cuda()
+    net(torch.rand(2, 28, 28, 1, device="cuda"))
+    with torch.no_grad():
+        net.d1.nested_q_w_layer.scale.fill_(1e-3)
+    log_scripts.save_compress_parameters(net, str(tmp_path))
+    w = np.load(tmp_path / "weights.npy", allow_pickle=True).item()
+    assert sorted(w) == ["custom_dense_layer/W", "custom_dense_layer/b", "custom_dense_layer_1/W", "custom_dense_layer_1/b"] \
+        or len(w) == 4
+    k = [n for n in w if n.endswith("/W")][0]
+    W = net.d1.W.detach().cpu().numpy()
+    want = np.floor(W / net.d1.nested_q_w_layer.scale.detach().cpu().numpy()).astype(np.int64).astype(np.int8)
+    assert w[k].dtype == np.int8 and np.array_equal(w[k], want)
+    with zipfile.ZipFile(tmp_path / "weights.zip") as z:
+        assert z.namelist() == ["weights.npy"]
+    lines = open(tmp_path / "file_sizes.log").read().splitlines()
+    assert lines[0].startswith("Weights size: ") and lines[1].startswith("Compressed weights size: ")
+    # the second dense layer still has the initial scale 1.19e-5: its codes overflow int8 and are reported
+    assert "custom_dense_layer" in open(tmp_path / "int8_overflow.log").read()
