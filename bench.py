@@ -198,6 +198,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import learned_quantization_b200 as lq
     ops = lq.ops
+    if args.only_qat:
+        q = run_qat(args, rank, world, local)
+        if rank == 0:
+            print(json.dumps(q))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     n = LAYOUT[0] * LAYOUT[1] * LAYOUT[2]
     P_h, s_h, dy_h = synth(LAYOUT, 42 + rank)
@@ -220,9 +227,39 @@ def run_ours(args):
     def fwd(P):
         check(lib.lq_fq_fwd(P.data_ptr(), s.data_ptr(), y.data_ptr(), None, 0, *LAYOUT, 0, ninf, pinf, stream))
 
+    # N > 1: ONE tensor [256 * world, 512, 512] sharded along `outer`.  Each rank runs the
+    # same single-pass kernels on its shard; the per-group statistics (24 * C bytes per rank) are
+    # gathered over our NCCL communicator and folded in shard order on a side stream, overlapping the
+    # next forward.  ds is identical on every rank and equals the unsharded result.
+    comm = side = None
+    if world > 1:
+        from learned_quantization_b200.training.dp import NcclComm
+        comm = NcclComm()
+        side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        stats = [torch.empty((LAYOUT[1], 3), dtype=torch.float64, device="cuda") for _ in range(2)]
+        gathered = [torch.empty((world, LAYOUT[1], 3), dtype=torch.float64, device="cuda") for _ in range(2)]
+        ev_stats = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        n_per_group = float(LAYOUT[0] * world * LAYOUT[2])
+        step_no = [0]
+
     def bwd(P, dy):
-        check(lib.lq_fq_bwd_threshold(dy.data_ptr(), P.data_ptr(), s.data_ptr(), LAMBDA, dX.data_ptr(), ds.data_ptr(),
-                                      *LAYOUT, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+        if world == 1:
+            check(lib.lq_fq_bwd_threshold(dy.data_ptr(), P.data_ptr(), s.data_ptr(), LAMBDA, dX.data_ptr(), ds.data_ptr(),
+                                          *LAYOUT, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+            return
+        k = step_no[0] % 2
+        step_no[0] += 1
+        main.wait_event(ev_done[k])                  # the gather of two steps ago has consumed stats[k]
+        check(lib.lq_fq_bwd_threshold_stats(dy.data_ptr(), P.data_ptr(), s.data_ptr(), LAMBDA, dX.data_ptr(),
+                                            stats[k].data_ptr(), *LAYOUT, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+        ev_stats[k].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_stats[k])
+            comm.allgather_f64(stats[k], gathered[k])
+            ops.fq_bwd_threshold_finish(gathered[k], LAMBDA, n_per_group, out=ds)
+            ev_done[k].record(side)
 
     def barrier():
         if world > 1:
@@ -282,7 +319,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "layout": list(LAYOUT),
                        "elements_per_gpu": n, "lambda": LAMBDA, "l2": "inputs_exceed_l2 (3 x 256 MiB arrays per pass, 2 input sets alternated)",
-                       "bytes_per_element": {"fwd": BYTES_FWD, "bwd": BYTES_BWD}, "dX": "written (not aliased to dy)"},
+                       "bytes_per_element": {"fwd": BYTES_FWD, "bwd": BYTES_BWD}, "dX": "written (not aliased to dy)",
+                       "sharding": "single device" if world == 1 else
+                       f"one tensor [{LAYOUT[0] * world},{LAYOUT[1]},{LAYOUT[2]}] sharded along outer over {world} ranks; "
+                       f"per-group statistics ({24 * LAYOUT[1]} B per rank) all-gathered per step on a side stream"},
             "elements_per_s": n * world / (step_ms * 1e-3),
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
@@ -294,11 +334,15 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n + 4 * LAYOUT[1],
                     "d2h_bytes_per_step": 4 * n + 4 * LAYOUT[1],
                     "api": "lq_host_fq_fwd_bwd (pinned host P, s, dy in; host y, ds out; dX is dy itself)"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": (3 if world == 1 else 4) * args.steps,
             "clocks": clocks,
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.close()
+        comm = None
     qat = None
     if not args.no_qat:
         del sets, y, dX, hP, hdy, hy, hws
@@ -486,13 +530,25 @@ def run_sweep(args):
         torch.cuda.empty_cache()
 
 
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version
+    banner to fd 1 when NCCL_DEBUG is set in the environment): point fd 1 at stderr for the run and
+    keep a private handle on the real stdout for the JSON lines."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w", buffering=1)
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-qat", action="store_true", help="skip the QAT images/s section of the line")
+    ap.add_argument("--only-qat", action="store_true", help="debug: run only the QAT section and print it")
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)

@@ -96,6 +96,20 @@ int lq_fq_bwd_threshold(const float* dy, const float* P, const float* s, float p
                         int round_mode, float qmin, float qmax,
                         void* ws, size_t ws_bytes, lq_stream_t stream);
 
+/* a2 for a tensor SHARDED along `outer` over several devices (microbench sizes):
+ * each shard runs lq_fq_bwd_threshold_stats on its slice -- same single HBM pass, but the second
+ * stage stops at the raw per-group statistics stats[3*g .. 3*g+2] = {sum, n_below, max|q|}
+ * (doubles) -- the shards' statistics are gathered (lq_dp_allgather_f64: 24*C bytes per rank, the
+ * path's only exchange), and lq_fq_bwd_threshold_finish folds them in shard order and applies
+ * NQ:103-116 with n_per_group = elements per group over ALL shards.  Every rank obtains the same
+ * bits, equal to the unsharded lq_fq_bwd_threshold up to the fp64 summation order. */
+int lq_fq_bwd_threshold_stats(const float* dy, const float* P, const float* s, float penalty_threshold,
+                              float* dX, double* stats, int64_t outer, int64_t C, int64_t inner,
+                              int round_mode, float qmin, float qmax,
+                              void* ws, size_t ws_bytes, lq_stream_t stream);
+int lq_fq_bwd_threshold_finish(const double* stats, int nshards, int64_t C, float penalty_threshold,
+                               double n_per_group, float* ds, lq_stream_t stream);
+
 /* a3 backward, CL:61-62 / PI:62-64:  dX = dy (copy skipped when NULL or aliased), ds = 0. */
 int lq_fq_bwd_ste(const float* dy, float* dX, float* ds, int64_t n_elems, int64_t C,
                   lq_stream_t stream);
@@ -192,6 +206,7 @@ int lq_dp_unique_id(void* out_id128);                       /* 128-byte ncclUniq
 int lq_dp_init(const void* id128, int rank, int world, lq_dp_t** out);
 int lq_dp_allreduce(lq_dp_t* dp, float* flat, int64_t n, float scale, lq_stream_t stream);
 int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_stream_t stream);
+int lq_dp_allgather_f64(lq_dp_t* dp, const double* send, double* recv /* [world*n] */, int64_t n, lq_stream_t stream);
 int lq_dp_destroy(lq_dp_t* dp);
 
 #ifdef __cplusplus

@@ -54,6 +54,8 @@ SIGNATURES = {
     "lq_workspace_bytes": (_I, [_DESCS, _I, _I, C.POINTER(_SZ)]),
     "lq_fq_fwd": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _F, _F, _P]),
     "lq_fq_bwd_threshold": (_I, [_P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _SZ, _P]),
+    "lq_fq_bwd_threshold_stats": (_I, [_P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _SZ, _P]),
+    "lq_fq_bwd_threshold_finish": (_I, [_P, _I, _I64, _F, C.c_double, _P, _P]),
     "lq_fq_bwd_ste": (_I, [_P, _P, _P, _I64, _I64, _P]),
     "lq_scale_constraint": (_I, [_P, _I64, _F, _P]),
     "lq_penalty_fwd": (_I, [_I, _DESCS, _I, _P, _P, _SZ, _P]),
@@ -71,6 +73,7 @@ SIGNATURES = {
     "lq_dp_init": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "lq_dp_allreduce": (_I, [_P, _P, _I64, _F, _P]),
     "lq_dp_allreduce_max": (_I, [_P, _P, _I64, _P]),
+    "lq_dp_allgather_f64": (_I, [_P, _P, _P, _I64, _P]),
     "lq_dp_destroy": (_I, [_P]),
 }
 

@@ -15,7 +15,7 @@ namespace lq {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat32 = 7 };
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };
 enum { ncclSum = 0, ncclMax = 2, ncclAvg = 4 };
 
 struct NcclApi {
@@ -24,6 +24,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -42,8 +43,9 @@ static void load_nccl() {
   g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllGather");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
-  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce;
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.AllGather;
 }
 
 static int need_nccl() {
@@ -136,6 +138,14 @@ extern "C" int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_strea
   if (n == 0) return LQ_OK;
   if (!flat) { set_error("lq_dp_allreduce_max: null buffer"); return LQ_E_NULLPTR; }
   return nccl_fail(g_nccl.AllReduce(flat, flat, (size_t)n, ncclFloat32, ncclMax, dp->comm, (cudaStream_t)stream), "ncclAllReduce(max)");
+}
+
+extern "C" int lq_dp_allgather_f64(lq_dp_t* dp, const double* send, double* recv, int64_t n, lq_stream_t stream) {
+  if (!dp) { set_error("lq_dp_allgather_f64: null communicator"); return LQ_E_NULLPTR; }
+  if (n < 0) { set_error("lq_dp_allgather_f64: n < 0"); return LQ_E_BADSHAPE; }
+  if (n == 0) return LQ_OK;
+  if (!send || !recv) { set_error("lq_dp_allgather_f64: null buffer"); return LQ_E_NULLPTR; }
+  return nccl_fail(g_nccl.AllGather(send, recv, (size_t)n, ncclFloat64, dp->comm, (cudaStream_t)stream), "ncclAllGather");
 }
 
 extern "C" int lq_dp_destroy(lq_dp_t* dp) {

@@ -194,7 +194,7 @@ static BwdThresholdOp<EXT> make_bwd_op(const QMode& qm, float lam) {
 // ------------------------------------------------------------------ K4 second stage
 // One block per group.  Walks the group's partials in index order with a fixed
 // thread->partial assignment, then a fixed shuffle/shared-memory tree: deterministic.
-enum { FIN_THRESHOLD = 0 };
+enum { FIN_THRESHOLD = 0, FIN_STATS = 1 };   // STATS: write raw {sum, count, max|q|} as doubles (sharded tensors)
 
 // Intermediate level for groups with very many first-level partials (per-tensor scales on
 // large tensors: one group, N/2048 partials): block (g, m) folds partials [m*kFinChunk,
@@ -267,6 +267,11 @@ __device__ __forceinline__ void finalize_group(const FinJob& f, long long g) {
     for (int i = 1; i < kFinThreads / 32; ++i) { sum += ssum[i]; cnt += scnt[i]; mx = fmaxf(mx, smx[i]); }
     // NQ:103-116: all above -> every element contributes c0 = -|tanh(lambda)| (mean = c0),
     // otherwise the mean of the below-threshold terms over ALL N_g elements; times max|q|.
+    if (f.mode == FIN_STATS) {
+      double* st = reinterpret_cast<double*>(f.ds) + 3 * g;
+      st[0] = sum; st[1] = (double)cnt; st[2] = (double)mx;
+      return;
+    }
     const double n_g = (double)f.outer * (double)f.inner;
     const float mean = (cnt == 0ull) ? f.p1 : (float)(sum / n_g);
     f.ds[g] = __fmul_rn(mean, mx);
@@ -336,8 +341,25 @@ int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const
   return launch_job(j, make_bwd_op<false>(qm, lam), st);
 }
 
-int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st) {
+// Combine the raw statistics of `nshards` shards of one tensor (fixed shard order: every rank
+// that holds the same gathered buffer computes bit-identical ds) and apply NQ:103-116.
+__global__ void __launch_bounds__(128) finish_shards_kernel(const double* stats, int nshards, long long C, float c0,
+                                                            double n_per_group, float* ds) {
+  cudaGridDependencySynchronize();     // launched with launch_after: wait for the gather before it in the stream
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= C) return;
+  double sum = 0.0, cnt = 0.0, mx = 0.0;
+  for (int r = 0; r < nshards; ++r) {
+    const double* st = stats + ((long long)r * C + g) * 3;
+    sum += st[0]; cnt += st[1]; mx = fmax(mx, st[2]);
+  }
+  const float mean = (cnt == 0.0) ? c0 : (float)(sum / n_per_group);
+  ds[g] = __fmul_rn(mean, (float)mx);
+}
+
+int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st, int mode) {
   FinJob f = make_fin(g, part, ds, s, lam);
+  f.mode = mode;
   if (g.nlin) {   // two-level second stage
     if (g.C * g.nlin > 0x7fffffffll) { set_error("too many intermediate partials"); return LQ_E_BADSHAPE; }
     int rc = launch_after(fold_partials_kernel, dim3((unsigned)(g.C * g.nlin)), dim3(256), st, "fold launch", f);
@@ -395,7 +417,45 @@ extern "C" int lq_fq_bwd_threshold(const float* dy, const float* P, const float*
   }
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = fq_bwd_elements_launch(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
-  return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), ds, s, penalty_threshold, st);
+  return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), ds, s, penalty_threshold, st, FIN_THRESHOLD);
+}
+
+extern "C" int lq_fq_bwd_threshold_stats(const float* dy, const float* P, const float* s, float penalty_threshold,
+                                         float* dX, double* stats, int64_t outer, int64_t C, int64_t inner,
+                                         int round_mode, float qmin, float qmax,
+                                         void* ws, size_t ws_bytes, lq_stream_t stream) {
+  int rc = check_dims(outer, C, inner);
+  if (rc) return rc;
+  if (!dy || !P || !s || !stats) { set_error("lq_fq_bwd_threshold_stats: null dy/P/s/stats"); return LQ_E_NULLPTR; }
+  if (reinterpret_cast<uintptr_t>(stats) & 7u) { set_error("lq_fq_bwd_threshold_stats: stats must be 8-byte aligned"); return LQ_E_BADSHAPE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (outer * C * inner == 0) {
+    if (C > 0) return cuda_fail(cudaMemsetAsync(stats, 0, (size_t)C * 3 * sizeof(double), st), "zero stats");
+    return LQ_OK;
+  }
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  const bool wr = (dX != nullptr && dX != dy);
+  const bool al = aligned16(P) && aligned16(dy) && (!wr || aligned16(dX));
+  Geom g = make_geom(outer, C, inner, al);
+  if ((rc = check_blocks(g))) return rc;
+  const size_t need = align256((size_t)g.npartials * sizeof(float4));
+  if (!ws || ws_bytes < need || !aligned16(ws)) {
+    set_error("lq_fq_bwd_threshold_stats: workspace %zu B (16-B aligned) needed, got %zu", need, ws_bytes);
+    return LQ_E_WORKSPACE;
+  }
+  if ((rc = fq_bwd_elements_launch(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
+  return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), reinterpret_cast<float*>(stats), s, penalty_threshold, st, FIN_STATS);
+}
+
+extern "C" int lq_fq_bwd_threshold_finish(const double* stats, int nshards, int64_t C, float penalty_threshold,
+                                          double n_per_group, float* ds, lq_stream_t stream) {
+  if (nshards < 1 || C < 0 || !(n_per_group > 0.0)) { set_error("lq_fq_bwd_threshold_finish: bad nshards / C / n_per_group"); return LQ_E_BADSHAPE; }
+  if (C == 0) return LQ_OK;
+  if (!stats || !ds) { set_error("lq_fq_bwd_threshold_finish: null stats/ds"); return LQ_E_NULLPTR; }
+  const float c0 = -fabsf(tanhf(penalty_threshold));
+  return launch_after(finish_shards_kernel, dim3((unsigned)((C + 127) / 128)), dim3(128), (cudaStream_t)stream,
+                      "finish launch", stats, nshards, (long long)C, c0, n_per_group, ds);
 }
 
 extern "C" int lq_fq_bwd_ste(const float* dy, float* dX, float* ds, int64_t n_elems, int64_t C,

@@ -353,7 +353,7 @@ int fq_fwd_launch(const Geom& g, const float* P, const float* s, float* y, void*
                   const QMode& qm, cudaStream_t st);
 int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const float* s, float lam,
                            float* dX, float4* part, const QMode& qm, cudaStream_t st);
-int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st);
+int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st, int mode = 0);
 int check_blocks(const Geom& g);
 Job make_job(const Geom& g, const float* P, const float* s, const float* dy, float* y, float* dX,
              void* codes, int codes_dtype, float4* part);

@@ -151,6 +151,38 @@ def fq_bwd_threshold(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, penalty
     return (dy if dX is None else dX), ds
 
 
+def fq_bwd_threshold_stats(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, penalty_threshold: float,
+                           layout=None, *, write_dx: bool = False, stats: Optional[torch.Tensor] = None):
+    """One SHARD of a tensor split along `outer`: (dX, stats) with stats[g] = {sum, n_below, max|q|}
+    (float64 [C, 3]).  Gather the shards' stats and call fq_bwd_threshold_finish."""
+    _require_cuda(dy, P, s)
+    layout = layout or group_layout(P.shape, s.shape)
+    if stats is None:
+        stats = torch.empty((layout[1], 3), dtype=torch.float64, device=P.device)
+    dX = torch.empty_like(dy) if write_dx else None
+    need = workspace_bytes([make_desc(layout=layout)], _lib.LQ_PHASE_BWD)
+    ws = workspace(need, P.device)
+    with torch.cuda.device(P.device):
+        check(lib.lq_fq_bwd_threshold_stats(dy.data_ptr(), P.data_ptr(), s.data_ptr(), float(penalty_threshold),
+                                            None if dX is None else dX.data_ptr(), stats.data_ptr(),
+                                            layout[0], layout[1], layout[2], _lib.LQ_ROUND_FLOOR, NEG_INF, POS_INF,
+                                            ws.data_ptr(), ws.numel(), _stream()))
+    return (dy if dX is None else dX), stats
+
+
+def fq_bwd_threshold_finish(stats_all: torch.Tensor, penalty_threshold: float, n_per_group: float,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ds from the gathered statistics of all shards (float64 [nshards, C, 3], shard order fixed)."""
+    if not stats_all.is_cuda or stats_all.dtype != torch.float64 or not stats_all.is_contiguous() or stats_all.dim() != 3:
+        raise ValueError("stats_all must be a contiguous float64 CUDA tensor [nshards, C, 3]")
+    nshards, C = stats_all.shape[0], stats_all.shape[1]
+    ds = torch.empty(C, dtype=torch.float32, device=stats_all.device) if out is None else out
+    with torch.cuda.device(stats_all.device):
+        check(lib.lq_fq_bwd_threshold_finish(stats_all.data_ptr(), nshards, C, float(penalty_threshold),
+                                             float(n_per_group), ds.data_ptr(), _stream()))
+    return ds
+
+
 def fq_bwd_ste(dy: torch.Tensor, s: torch.Tensor):
     """(dX, ds) of CL:61-62 / PI:62-64: dX is dy, ds is zeros."""
     _require_cuda(dy, s)

@@ -73,6 +73,13 @@ class NcclComm(Comm):
     def allreduce_max_(self, flat: torch.Tensor) -> None:
         check(lib.lq_dp_allreduce_max(self._h, flat.data_ptr(), flat.numel(), torch.cuda.current_stream().cuda_stream))
 
+    def allgather_f64(self, send: torch.Tensor, recv: torch.Tensor) -> None:
+        """recv[r] = rank r's `send` (float64, CUDA): the exchange of the sharded threshold backward."""
+        if send.dtype != torch.float64 or recv.dtype != torch.float64 or recv.numel() != send.numel() * self.world:
+            raise ValueError("allgather_f64: float64 buffers, recv = world * send")
+        check(lib.lq_dp_allgather_f64(self._h, send.data_ptr(), recv.data_ptr(), send.numel(),
+                                      torch.cuda.current_stream().cuda_stream))
+
     def close(self):
         if self._h:
             check(lib.lq_dp_destroy(self._h))

@@ -124,7 +124,9 @@ class TrainStep:
     def _scale_backward(self):
         self.bank.backward(self.bucket.dy, self.bucket.ds)
 
-    def __call__(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+    # The step in three pieces, so that the collective can stay outside a CUDA graph:
+    def _forward_backward(self, x, y_true):
+        """forward, loss, autograd backward, gradients gathered into the flat bucket."""
         b, bucket = self.bank, self.bucket
         b.forward()
         for p in self.plain:
@@ -142,25 +144,39 @@ class TrainStep:
             extra_p = [(v, p.grad) for v, p in zip(bucket.dy, b.params) if p.grad is not None]
             if extra_p:
                 torch._foreach_add_([v for v, _ in extra_p], [g for _, g in extra_p])
-            exchange_gradients(bucket, self.comm, self._scale_backward, self.ds_mode)
+        return loss.detach()
+
+    def _update(self):
+        """penalty scale gradients, then the fused optimizer + constraint."""
+        b, bucket = self.bank, self.bucket
+        with torch.no_grad():
             extra_s = [(v, s.grad) for v, s in zip(bucket.ds, b.scales) if s.grad is not None]
             if extra_s:
                 torch._foreach_add_([v for v, _ in extra_s], [g.view(v.shape) for v, g in extra_s])
-            self.iterations += 1
             self._step_dev.add_(1)
             if self.optimizer == "adam":
                 ops.opt_adam(self.table, self.lr, self._step_dev)
             else:
                 ops.opt_sgd(self.table, self.lr, self.momentum, self.nesterov)
-        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+        loss = self._forward_backward(x, y_true)
+        with torch.no_grad():
+            exchange_gradients(self.bucket, self.comm, self._scale_backward, self.ds_mode)
+        self._update()
+        self.iterations += 1
+        return loss
 
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, x: torch.Tensor, y_true: torch.Tensor, warmup: int = 3) -> None:
-        """Capture the whole step (forward, autograd backward, gradient exchange, fused optimizer) in
-        ONE CUDA graph: the step issues several hundred small launches (cuDNN, BatchNorm, our
-        multi-tensor kernels, NCCL) and is otherwise bounded by the host's launch rate.  Everything
-        the step changes between iterations lives in device memory (Adam's t included), so a replay
-        is exact.  `x`, `y_true` fix the static input shapes; replay() copies new batches into them."""
+        """Capture the step in CUDA graphs: it issues several hundred small launches (cuDNN, BatchNorm,
+        our multi-tensor kernels) and is otherwise bounded by the host's launch rate.  Everything the
+        step changes between iterations lives in device memory (Adam's t included), so a replay is
+        exact.  Single device: ONE graph for the whole step.  Data parallel: three graphs
+        (forward+backward | scale backward | update) with the NCCL collective launched between them
+        from the host -- capturing the collective itself deadlocked at replay on this stack
+        (NCCL 2.28.9, 2 x B200), so it stays outside.
+        `x`, `y_true` fix the static input shapes; replay() copies new batches into them."""
         self._sx, self._sy = x.clone(), y_true.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -169,10 +185,22 @@ class TrainStep:
                 self(self._sx, self._sy)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._sloss = self(self._sx, self._sy)
-        self._graph = g
+        if self.comm.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._sloss = self(self._sx, self._sy)
+            self.iterations -= 1                     # recording does not execute
+            self._graph = (g,)
+            return
+        ga, gs, gu = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            self._sloss = self._forward_backward(self._sx, self._sy)
+        pool = ga.pool()
+        with torch.cuda.graph(gs, pool=pool):
+            self._scale_backward()
+        with torch.cuda.graph(gu, pool=pool):
+            self._update()
+        self._graph = (ga, gs, gu)
 
     def replay(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
         """One captured step on a new batch (device or pinned-host tensors of the captured shapes)."""
@@ -180,6 +208,12 @@ class TrainStep:
             raise RuntimeError("call capture() first")
         self._sx.copy_(x, non_blocking=True)
         self._sy.copy_(y_true, non_blocking=True)
-        self._graph.replay()
+        if len(self._graph) == 1:
+            self._graph[0].replay()
+        else:
+            ga, gs, gu = self._graph
+            ga.replay()
+            exchange_gradients(self.bucket, self.comm, gs.replay, self.ds_mode)
+            gu.replay()
         self.iterations += 1
         return self._sloss

@@ -266,6 +266,33 @@ def test_hoisted_reciprocal_division_is_ieee_division(lq):
     assert (bad, seen) == (0, 0)
 
 
+@pytest.mark.parametrize("shape,s_shape,nshards", [((8, 16, 256), (1, 16, 1), 4), ((6, 1, 9000), (1, 1, 1), 3),
+                                                   ((640, 12, 1), (1, 12, 1), 5), ((8, 16, 256), (1, 16, 1), 1)])
+def test_sharded_backward_equals_unsharded(lq, shape, s_shape, nshards):
+    """a tensor split along `outer`; per-shard statistics + one gather + finish == the
+    single-device backward on the whole tensor (and the oracle)."""
+    ops = lq.ops
+    rng = np.random.default_rng(21)
+    P = rng.normal(0, 0.05, shape).astype(np.float32)
+    dy = rng.normal(0, 1e-3, shape).astype(np.float32)
+    s = rng.uniform(5e-3, 2e-2, s_shape).astype(np.float32)
+    for lam in (1e-3, 0.0, 1e3):
+        q_ref, y_ref = o.fq_forward(P, s)
+        _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, lam, accum="fp64")
+        _, ds_whole = ops.fq_bwd_threshold(dev(dy), dev(P), dev(s), lam)
+        cuts = np.linspace(0, shape[0], nshards + 1).astype(int)
+        stats = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            Pa, da = dev(P[a:b]), dev(dy[a:b])
+            dX, st = ops.fq_bwd_threshold_stats(da, Pa, dev(s), lam, (int(b - a), shape[1], shape[2]), write_dx=True)
+            assert bits_equal(host(dX), dy[a:b])
+            stats.append(st)
+        n_per_group = shape[0] * shape[2]
+        ds = ops.fq_bwd_threshold_finish(torch.stack(stats).contiguous(), lam, n_per_group)
+        assert ds_close(host(ds), host(ds_whole).reshape(-1), tol=1e-6)
+        assert ds_close(host(ds), ds_ref.reshape(-1))
+
+
 def test_unaligned_pointers_take_scalar_path(lq):
     ops = lq.ops
     rng = np.random.default_rng(5)

@@ -173,8 +173,19 @@ def test_mnist_step_trains_and_keeps_scales_above_floor(lq):
         assert float(s.min()) >= float(o.SCALE_INIT)
 
 
-def test_graph_replay_equals_eager_steps(lq):
-    """A captured step replayed N times == N eager steps (same parameters, Adam slots and t)."""
+@pytest.mark.parametrize("split", [False, True])
+def test_graph_replay_equals_eager_steps(lq, split):
+    """A captured step replayed N times == N eager steps (same parameters, Adam slots and t).
+    split=True drives the data-parallel form (three graphs, collective between them) with a
+    world-2 communicator whose allreduce is the identity."""
+    from learned_quantization_b200.training.dp import Comm
+
+    class _Loopback(Comm):
+        world, rank = 2, 0
+
+        def allreduce_mean_(self, flat):
+            return None
+
     from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
         sparse_categorical_crossentropy as scce
@@ -188,7 +199,7 @@ def test_graph_replay_equals_eager_steps(lq):
         net = _TinyNet(nq, 1e-3, "channelwise").cuda()
         net(x)
         nets.append(net)
-    eager, graphed = (TrainStep(n, scce, optimizer="adam", lr=1e-3) for n in nets)
+    eager, graphed = (TrainStep(n, scce, optimizer="adam", lr=1e-3, comm=(_Loopback() if split else None)) for n in nets)
     graphed.capture(x, y, warmup=2)                    # 2 warm-up steps + 1 captured-while-recording (not executed)
     for _ in range(3):
         graphed.replay(x, y)
