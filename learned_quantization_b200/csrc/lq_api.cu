@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <mutex>
 #include "lq_common.cuh"
+#include "lq_col_tma.cuh"
 
 namespace lq {
 
@@ -86,7 +87,11 @@ extern "C" int lq_workspace_bytes(const lq_tensor_desc* descs, int n, int phase,
     // larger of the two possible layouts so any pointer alignment fits.
     const Geom a = make_geom(descs[i].outer, descs[i].C, descs[i].inner, true);
     const Geom b = make_geom(descs[i].outer, descs[i].C, descs[i].inner, false);
-    const long long slots = a.npartials > b.npartials ? a.npartials : b.npartials;
+    long long slots = a.npartials > b.npartials ? a.npartials : b.npartials;
+    if (col_tma_shape_ok(descs[i].outer, descs[i].C, descs[i].inner)) {
+      const long long t = make_col_tma_geom(descs[i].outer, descs[i].C, descs[i].inner).npartials;
+      if (t > slots) slots = t;
+    }
     if (phase == LQ_PHASE_BWD) total += align256((size_t)slots * sizeof(float4));
     else if (phase == LQ_PHASE_PENALTY_FWD || phase == LQ_PHASE_PENALTY_BWD)
       total += align256((size_t)slots * sizeof(float4)) + align256((size_t)descs[i].C * sizeof(float4));

@@ -2,6 +2,7 @@
 // and their multi-tensor forms (K5).  Reference semantics: NQ:49-120 (see include/lq.h).
 #include <math.h>
 #include "lq_traverse.cuh"
+#include "lq_col_tma.cuh"
 
 namespace lq {
 
@@ -334,6 +335,23 @@ int fq_fwd_launch(const Geom& g, const float* P, const float* s, float* y, void*
   return launch_job(j, op, st);
 }
 
+// Geometry of the threshold backward for one tensor: TMA-staged COL kernel when the shape and the
+// pointers allow it, otherwise ROW / register COL.  `tma` tells fq_bwd_elements_launch which.
+Geom bwd_geom(long long outer, long long C, long long inner, const float* dy, const float* P, const float* dX, bool* tma) {
+  const bool wr = (dX != nullptr && dX != dy);
+  const bool al = aligned16(P) && aligned16(dy) && (!wr || aligned16(dX));
+  *tma = al && col_tma_shape_ok(outer, C, inner);
+  if (*tma) return make_col_tma_geom(outer, C, inner);
+  // register COL: the backward takes the one-column-per-thread traversal (run_col1)
+  return make_geom(outer, C, inner, al && inner >= kRowMinInner);
+}
+
+int fq_bwd_col_tma_launch(const Geom& g, const float* dy, const float* P, const float* s, float lam,
+                          float* dX, float4* part, const QMode& qm, cudaStream_t st) {
+  if (qm.ext) return col_tma_launch(g, dy, P, s, dX, part, make_bwd_op<true>(qm, lam), st);
+  return col_tma_launch(g, dy, P, s, dX, part, make_bwd_op<false>(qm, lam), st);
+}
+
 int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const float* s, float lam,
                            float* dX, float4* part, const QMode& qm, cudaStream_t st) {
   Job j = make_job(g, P, s, dy, nullptr, dX, nullptr, 0, part);
@@ -406,9 +424,8 @@ extern "C" int lq_fq_bwd_threshold(const float* dy, const float* P, const float*
   if (outer * C * inner == 0) return LQ_OK;
   QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
   if (rc) return rc;
-  const bool wr = (dX != nullptr && dX != dy);
-  const bool al = aligned16(P) && aligned16(dy) && (!wr || aligned16(dX));
-  Geom g = make_geom(outer, C, inner, al);
+  bool tma = false;
+  Geom g = bwd_geom(outer, C, inner, dy, P, dX, &tma);
   if ((rc = check_blocks(g))) return rc;
   const size_t need = align256((size_t)g.npartials * sizeof(float4));
   if (!ws || ws_bytes < need || !aligned16(ws)) {
@@ -416,7 +433,7 @@ extern "C" int lq_fq_bwd_threshold(const float* dy, const float* P, const float*
     return LQ_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = fq_bwd_elements_launch(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
+  if ((rc = (tma ? fq_bwd_col_tma_launch : fq_bwd_elements_launch)(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
   return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), ds, s, penalty_threshold, st, FIN_THRESHOLD);
 }
 
@@ -435,16 +452,15 @@ extern "C" int lq_fq_bwd_threshold_stats(const float* dy, const float* P, const 
   }
   QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
   if (rc) return rc;
-  const bool wr = (dX != nullptr && dX != dy);
-  const bool al = aligned16(P) && aligned16(dy) && (!wr || aligned16(dX));
-  Geom g = make_geom(outer, C, inner, al);
+  bool tma = false;
+  Geom g = bwd_geom(outer, C, inner, dy, P, dX, &tma);
   if ((rc = check_blocks(g))) return rc;
   const size_t need = align256((size_t)g.npartials * sizeof(float4));
   if (!ws || ws_bytes < need || !aligned16(ws)) {
     set_error("lq_fq_bwd_threshold_stats: workspace %zu B (16-B aligned) needed, got %zu", need, ws_bytes);
     return LQ_E_WORKSPACE;
   }
-  if ((rc = fq_bwd_elements_launch(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
+  if ((rc = (tma ? fq_bwd_col_tma_launch : fq_bwd_elements_launch)(g, dy, P, s, penalty_threshold, dX, reinterpret_cast<float4*>(ws), qm, st))) return rc;
   return fq_finalize_launch(g, reinterpret_cast<const float4*>(ws), reinterpret_cast<float*>(stats), s, penalty_threshold, st, FIN_STATS);
 }
 
@@ -529,7 +545,8 @@ extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_th
       if (d.outer * d.C * d.inner == 0) continue;
       if (!d.P || !d.s || !d.dy || !d.ds) { set_error("lq_mt_fq_bwd: desc %d has null P/s/dy/ds", i); return LQ_E_NULLPTR; }
       const bool wr = (d.dX != nullptr && d.dX != d.dy);
-      Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dy) && (!wr || aligned16(d.dX)));
+      Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dy) && (!wr || aligned16(d.dX)) &&
+                                                d.inner >= kRowMinInner);
       if ((rc = check_blocks(g))) return rc;
       const size_t need = align256((size_t)g.npartials * sizeof(float4));
       if (!ws || off + need > ws_bytes) {

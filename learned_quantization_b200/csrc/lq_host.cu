@@ -31,7 +31,7 @@ struct HostPlan {
 
 static HostPlan make_plan(long long outer, long long C, long long inner) {
   HostPlan p{};
-  const Geom G = make_geom(outer, C, inner, true);
+  const Geom G = make_geom(outer, C, inner, inner >= kRowMinInner);
   const long long n = outer * C * inner;
   if (outer > 1) {
     p.mode = 0;
@@ -48,7 +48,7 @@ static HostPlan make_plan(long long outer, long long C, long long inner) {
     p.mode = 1;
     p.step = std::min(C, std::max(1ll, kChunkElems / inner));
     p.chunk_elems = p.step * inner;
-    p.npart = kSlots * make_geom(1, p.step, inner, true).npartials;   // per-slot private partials
+    p.npart = kSlots * make_geom(1, p.step, inner, inner >= kRowMinInner).npartials;   // per-slot private partials
   } else {
     p.mode = 2;
     long long step = std::max(kChunkElems / kSeg * kSeg, (long long)kSegMax + kSeg);
@@ -123,7 +123,7 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
   LQ_TRY(cudaEventRecord(ev_s, st[0]), "event record");
   for (int i = 1; i < kSlots; ++i) LQ_TRY(cudaStreamWaitEvent(st[i], ev_s, 0), "stream wait");
 
-  const Geom G = make_geom(outer, C, inner, true);
+  const Geom G = make_geom(outer, C, inner, inner >= kRowMinInner);
   const long long axis_len = (p.mode == 0) ? outer : (p.mode == 1 ? C : n);
   int k = 0;
   for (long long a0 = 0, a_next = 0; a0 < axis_len; a0 = a_next, ++k) {
@@ -150,7 +150,7 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
     float* dY = stage_ptr(slot, 2);
     LQ_TRY(cudaMemcpyAsync(dP, hP + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D P");
     LQ_TRY(cudaMemcpyAsync(ddy, hdy + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D dy");
-    const Geom g = make_geom(co, cc, ci, true);
+    const Geom g = make_geom(co, cc, ci, ci >= kRowMinInner);
     LQ_TRY_RC(fq_fwd_launch(g, dP, s_ptr, dY, nullptr, 0, qm, st[slot]));
     LQ_TRY_RC(fq_bwd_elements_launch(g, ddy, dP, s_ptr, penalty_threshold, nullptr, part_ptr, qm, st[slot]));
     LQ_TRY(cudaMemcpyAsync(hy + e0, dY, (size_t)ne * 4, cudaMemcpyDeviceToHost, st[slot]), "D2H y");

@@ -202,6 +202,10 @@ LAYOUTS = [
     ((128, 10), (1, 10)), ((128, 10), (128, 1)), ((37, 5, 131), (1, 5, 1)), ((9, 6, 4100), (1, 6, 1)),
     ((2, 3, 10001), (1, 3, 1)), ((1000, 3), (1, 3)), ((513, 7, 2), (1, 7, 1)), ((5,), (1,)), ((1,), (1,)),
     ((64, 1024), (1, 1024)), ((300, 260, 4), (1, 260, 1)), ((16, 2048, 128), (1, 2048, 1)),
+    # TMA-staged COL backward (outer >= 512, W % 4 == 0, >= 1 Mi elements): full / partial column tiles,
+    # 32-, 64- and 128-column tiles, row tails, inner > 1
+    ((4100, 260), (1, 260)), ((2100, 64, 8), (1, 64, 1)), ((27000, 10, 4), (1, 10, 1)), ((1030, 1024), (1, 1024)),
+    ((16500, 64), (1, 64)), ((9000, 128), (1, 128)),
 ]
 
 
