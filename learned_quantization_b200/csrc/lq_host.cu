@@ -38,7 +38,7 @@ static HostPlan make_plan(long long outer, long long C, long long inner) {
     const long long slice = C * inner;
     long long step = std::max(1ll, kChunkElems / slice);
     if (G.regime == REG_COL) {
-      const long long R = std::max((long long)G.by * 16, 64ll);
+      const long long R = G.rpc;
       step = std::max(R, step / R * R);
     }
     p.step = std::min(step, outer);
@@ -136,7 +136,7 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
     if (p.mode == 0) {
       e0 = a0 * C * inner; ne = (a1 - a0) * C * inner; co = a1 - a0; cc = C; ci = inner;
       part_ptr = d_part + ((G.regime == REG_ROW) ? a0 * C * G.nseg
-                                                 : (a0 / std::max((long long)G.by * 16, 64ll)) * G.W);
+                                                 : (a0 / (long long)G.rpc) * G.W);
     } else if (p.mode == 1) {
       e0 = a0 * inner; ne = (a1 - a0) * inner; co = 1; cc = a1 - a0; ci = inner;
       s_ptr = d_s + a0;
@@ -150,7 +150,7 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
     float* dY = stage_ptr(slot, 2);
     LQ_TRY(cudaMemcpyAsync(dP, hP + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D P");
     LQ_TRY(cudaMemcpyAsync(ddy, hdy + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D dy");
-    const Geom g = make_geom(co, cc, ci, ci >= kRowMinInner);
+    const Geom g = make_geom(co, cc, ci, ci >= kRowMinInner, (p.mode == 0 && G.regime == REG_COL) ? G.rpc : 0);
     LQ_TRY_RC(fq_fwd_launch(g, dP, s_ptr, dY, nullptr, 0, qm, st[slot]));
     LQ_TRY_RC(fq_bwd_elements_launch(g, ddy, dP, s_ptr, penalty_threshold, nullptr, part_ptr, qm, st[slot]));
     LQ_TRY(cudaMemcpyAsync(hy + e0, dY, (size_t)ne * 4, cudaMemcpyDeviceToHost, st[slot]), "D2H y");
