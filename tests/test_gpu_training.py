@@ -278,3 +278,73 @@ def test_save_compress_parameters_writes_the_reference_artefacts(lq, tmp_path):
     assert lines[0].startswith("Weights size: ") and lines[1].startswith("Compressed weights size: ")
     # the second dense layer still has the initial scale 1.19e-5: its codes overflow int8 and are reported
     assert "custom_dense_layer" in open(tmp_path / "int8_overflow.log").read()
+
+
+# ------------------------------------------------------------------ the other two variants through TrainStep
+class _TinyNetCL(torch.nn.Module):
+    """custom_loss_terms variant: STE layers (ds = 0 from the operator), scale gradients from the loss term."""
+
+    def __init__(self, L, orientation):
+        super().__init__()
+        from learned_quantization_b200 import RandomNormal
+        init = RandomNormal(seed=4)
+        self.c1 = L.CustomConv2DLayer(seed=4, penalty_rate=1e-3, orientation=orientation, initializer=init, filters=8,
+                                      kernel_size=(3, 3), strides=(1, 1), padding="same", name="a", regularizer=None)
+        self.fc = L.CustomDenseLayer(seed=4, units=10, penalty_rate=1e-3, orientation="rowwise", initializer=init,
+                                     name="fc", regularizer=None)
+
+    def forward(self, x):
+        return torch.softmax(self.fc(torch.relu(self.c1(x)).mean(dim=(1, 2))), dim=-1)
+
+
+@pytest.mark.parametrize("cls_name", ["SCCEMaxBin", "SCCEDifference", "SCCEInverse"])
+def test_custom_loss_variant_step_equals_per_layer_autograd(lq, cls_name, tmp_path):
+    """IMAGENETTE/custom_loss_terms/experiment.py:784-793: loss = scce + gamma * penalty(P, s).  Through the
+    bank, dP = dy (STE) + penalty gradient, ds = penalty gradient; must equal the per-layer autograd path."""
+    from learned_quantization_b200.custom_loss_terms.custom_components import custom_layers as cl
+    from learned_quantization_b200.custom_loss_terms.custom_components import custom_loss_functions as lf
+    from learned_quantization_b200.training.step import TrainStep
+    torch.manual_seed(0)
+    net = _TinyNetCL(cl, "channelwise").cuda()
+    x = torch.rand(4, 10, 10, 3, device="cuda") * 255.0
+    y = torch.randint(0, 10, (4,), device="cuda")
+    net(x)
+    with torch.no_grad():
+        for q in (net.c1.nested_q_k_layer, net.c1.nested_q_b_layer, net.fc.nested_q_w_layer, net.fc.nested_q_b_layer):
+            q.scale.uniform_(5e-3, 2e-2)
+    loss_obj = getattr(lf, cls_name)(layers=[net.c1, net.fc], penalty_rate=0.5, log_dir=str(tmp_path))
+    loss_obj.log_to_files = False
+    for p in net.parameters():
+        p.grad = None
+    loss_obj.compute_total_loss(y, net(x)).mean().backward()
+    ref = {id(p): (None if p.grad is None else p.grad.clone()) for p in net.parameters()}
+    step = TrainStep(net, loss_obj.compute_total_loss, optimizer="sgd", lr=0.0)     # lr 0: parameters stay put
+    step(x, y)
+    b = step.bucket
+    for v, p in list(zip(b.dy, step.bank.params)) + list(zip(b.ds, step.bank.scales)):
+        r = ref[id(p)]
+        r = torch.zeros_like(p) if r is None else r
+        a, rr = v.cpu().numpy().reshape(-1), r.cpu().numpy().reshape(-1)
+        assert float(np.max(np.abs(a - rr))) <= 1e-4 * max(float(np.max(np.abs(rr))), 1e-30), (cls_name, tuple(p.shape))
+    assert any(float(v.abs().max()) > 0 for v in b.ds), "the loss term must produce scale gradients"
+
+
+def test_paper_variant_step_with_sgd_nesterov(lq):
+    """CIFAR-10/paper_implementation: STE layers without conv bias, SGD(0.1, 0.9, nesterov, wd 5e-4)."""
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.training.step import TrainStep
+    torch.manual_seed(2)
+    net = models.cifar_resnet18(0.0, orientation="scalar").cuda().train()
+    x, y = models.synthetic_batch(8, (32, 32, 3), "cuda")
+    x = x / 255.0
+    net(x)
+    loss_fn = lambda yt, logits: scce(yt, torch.softmax(logits, dim=-1))
+    step = TrainStep(net, loss_fn, optimizer="sgd", lr=0.01, momentum=0.9, nesterov=True, weight_decay=5e-4)
+    assert len(step.bank.params) == 22 and step.bank.sgrad_mode == 0
+    before = [p.detach().clone() for p in step.bank.params[:3]]
+    losses = [float(step(x, y)) for _ in range(8)]
+    assert np.isfinite(losses).all()
+    assert all(float(v.abs().max()) == 0.0 for v in step.bucket.ds)        # PI:62-64: scale gradient is zeros
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(before, step.bank.params[:3]))
