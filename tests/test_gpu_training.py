@@ -1,5 +1,7 @@
 """GPU tier: the step after / around the hot path -- fused optimizer + constraint,
 the one-launch-per-phase QuantBank, the TrainStep, and the model builders' tensor inventories."""
+import os
+
 import numpy as np
 import pytest
 
@@ -348,3 +350,35 @@ def test_paper_variant_step_with_sgd_nesterov(lq):
     assert np.isfinite(losses).all()
     assert all(float(v.abs().max()) == 0.0 for v in step.bucket.ds)        # PI:62-64: scale gradient is zeros
     assert any(not torch.equal(a, p.detach()) for a, p in zip(before, step.bank.params[:3]))
+
+
+def test_tracking_callbacks_write_the_reference_log_files(lq, tmp_path):
+    """custom_callbacks.py:9-237: same files, same 'Epoch N' + value-per-line format, numbers from the device."""
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_callbacks as cb
+    from learned_quantization_b200.training import models
+    net = models.mnist_mlp(1e-10, orientation="rowwise").cuda()
+    net(torch.rand(2, 28, 28, 1, device="cuda"))
+    with torch.no_grad():
+        net.d1.nested_q_w_layer.scale.uniform_(5e-3, 2e-2)
+        net.d1.nested_q_b_layer.scale.fill_(1e-3)
+        net.d1.b.normal_(0, 0.05)
+    c = cb.NestedScaleTrackingCallback(net.d1, str(tmp_path))
+    c.on_train_begin()
+    c.on_epoch_end(0)
+    c.on_epoch_end(1)
+    c.on_train_end()
+    W = net.d1.W.detach().cpu().numpy()
+    q = np.floor(W / net.d1.nested_q_w_layer.scale.detach().cpu().numpy())
+    lines = open(c.log_file_path_qk_epoch).read().split()
+    assert lines == ["Epoch", "0", str(len(np.unique(q))), "Epoch", "1", str(len(np.unique(q)))]
+    mx = open(c.log_file_path_qk_epoch_max).read().splitlines()
+    assert mx[0] == "Epoch 0" and len(mx) == 2 * (1 + 784)
+    assert np.allclose([float(v) for v in mx[1:785]], np.max(np.abs(q), axis=1))
+    uniq = [l.split(", ") for l in open(c.log_file_path_qk_unique).read().splitlines()]
+    vals, cnts = np.unique(q.reshape(-1), return_counts=True)
+    assert [float(a) for a, _ in uniq] == list(vals.astype(float)) and [int(b) for _, b in uniq] == list(cnts)
+    assert len(open(c.log_file_path_qk).read().splitlines()) == q.size
+    assert os.path.basename(c.log_file_path_k_scale) == "Weights_(784, 128)_Rowwise-scaler_(784, 1).log"
+    a = cb.AccuracyLossTrackingCallBack(str(tmp_path))
+    a.on_epoch_end(0, {"val_accuracy": 0.5, "val_loss": 1.0, "accuracy": 0.25, "loss": 2.0})
+    assert open(tmp_path / "accuracy" / "train_accuracy.log").read() == "Epoch 0\n0.25\n"
