@@ -229,12 +229,16 @@ def run_ours(args):
 
     # N > 1: ONE tensor [256 * world, 512, 512] sharded along `outer`.  Each rank runs the
     # same single-pass kernels on its shard; the per-group statistics (24 * C bytes per rank) are
-    # gathered over our NCCL communicator and folded in shard order on a side stream, overlapping the
-    # next forward.  ds is identical on every rank and equals the unsharded result.
-    comm = side = None
+    # exchanged and folded in shard order by ONE kernel over NVLink peer memory
+    # (lq_fq_bwd_threshold_finish_p2p) on a side stream, overlapping the next forward.  ds is identical
+    # on every rank and equals the unsharded result; --exchange nccl uses lq_dp_allgather_f64 +
+    # lq_fq_bwd_threshold_finish instead, and the two are compared before timing.
+    comm = side = p2p = None
     if world > 1:
-        from learned_quantization_b200.training.dp import NcclComm
+        from learned_quantization_b200.training.dp import NcclComm, P2PFinish
         comm = NcclComm()
+        if args.exchange == "p2p":
+            p2p = P2PFinish(max_groups=LAYOUT[1])
         side = torch.cuda.Stream()
         main = torch.cuda.current_stream()
         stats = [torch.empty((LAYOUT[1], 3), dtype=torch.float64, device="cuda") for _ in range(2)]
@@ -257,9 +261,25 @@ def run_ours(args):
         ev_stats[k].record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev_stats[k])
-            comm.allgather_f64(stats[k], gathered[k])
-            ops.fq_bwd_threshold_finish(gathered[k], LAMBDA, n_per_group, out=ds)
+            if p2p is not None:
+                p2p.finish(stats[k], LAMBDA, n_per_group, ds)
+            else:
+                comm.allgather_f64(stats[k], gathered[k])
+                ops.fq_bwd_threshold_finish(gathered[k], LAMBDA, n_per_group, out=ds)
             ev_done[k].record(side)
+
+    if p2p is not None:          # the fused peer-memory path must reproduce the NCCL gather path bit for bit
+        P0, dy0 = sets[0]
+        st0 = torch.empty((LAYOUT[1], 3), dtype=torch.float64, device="cuda")
+        check(lib.lq_fq_bwd_threshold_stats(dy0.data_ptr(), P0.data_ptr(), s.data_ptr(), LAMBDA, dX.data_ptr(),
+                                            st0.data_ptr(), *LAYOUT, 0, ninf, pinf, ws.data_ptr(), ws.numel(), stream))
+        g0 = torch.empty((world, LAYOUT[1], 3), dtype=torch.float64, device="cuda")
+        comm.allgather_f64(st0, g0)
+        ds_nccl = ops.fq_bwd_threshold_finish(g0, LAMBDA, n_per_group)
+        ds_p2p = p2p.finish(st0, LAMBDA, n_per_group, torch.empty_like(ds_nccl))
+        torch.cuda.synchronize()
+        if p2p.timed_out() or not torch.equal(ds_nccl.view(torch.int32), ds_p2p.view(torch.int32)):
+            raise SystemExit("bench.py: peer-memory finish disagrees with the NCCL gather path")
 
     def barrier():
         if world > 1:
@@ -322,7 +342,9 @@ def run_ours(args):
                        "bytes_per_element": {"fwd": BYTES_FWD, "bwd": BYTES_BWD}, "dX": "written (not aliased to dy)",
                        "sharding": "single device" if world == 1 else
                        f"one tensor [{LAYOUT[0] * world},{LAYOUT[1]},{LAYOUT[2]}] sharded along outer over {world} ranks; "
-                       f"per-group statistics ({24 * LAYOUT[1]} B per rank) all-gathered per step on a side stream"},
+                       f"per-group statistics ({24 * LAYOUT[1]} B per rank) exchanged per step on a side stream by "
+                       + ("one fused peer-memory kernel over NVLink (checked against the NCCL gather before timing)"
+                          if p2p is not None else "lq_dp_allgather_f64")},
             "elements_per_s": n * world / (step_ms * 1e-3),
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
@@ -341,6 +363,11 @@ def run_ours(args):
             line["cpu_baseline"] = cb
     if comm is not None:
         torch.cuda.synchronize()
+        if p2p is not None:
+            if p2p.timed_out():
+                raise SystemExit("bench.py: a rank timed out in the peer-memory exchange")
+            dist.barrier()
+            p2p.close()
         comm.close()
         comm = None
     qat = None
@@ -553,6 +580,8 @@ def main():
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)
     ap.add_argument("--qat-eager", action="store_true", help="do not capture the QAT step in a CUDA graph")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the shards' statistics are exchanged (fused peer-memory kernel, or NCCL all-gather)")
     ap.add_argument("--sweep", action="store_true", help="layout/size sweep (one JSON line each) instead of the headline")
     ap.add_argument("--max-elems", type=int, default=1 << 28)
     ap.add_argument("--only", default="", help="comma-separated layout names for --sweep")

@@ -209,6 +209,22 @@ int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_stream_t stream)
 int lq_dp_allgather_f64(lq_dp_t* dp, const double* send, double* recv /* [world*n] */, int64_t n, lq_stream_t stream);
 int lq_dp_destroy(lq_dp_t* dp);
 
+/* The same exchange + finish as lq_dp_allgather_f64 + lq_fq_bwd_threshold_finish, fused into ONE
+ * kernel over NVLink peer memory: each rank stores its per-group statistics into every peer's
+ * receive buffer, publishes / awaits a per-step flag, and folds the world's statistics in rank order.
+ * lq_p2p_create allocates this rank's receive buffer (the one device allocation the library makes;
+ * cudaMalloc, so that it is IPC-exportable) and returns its 64-byte cudaIpcMemHandle; the host program
+ * gathers the handles of all ranks (world * 64 bytes, rank order) and passes them to lq_p2p_connect.
+ * One process per GPU.  lq_p2p_error reports (and synchronises for) the time-out flag a rank raises
+ * when a peer does not show up within ~2 s. */
+typedef struct lq_p2p lq_p2p_t;
+int lq_p2p_create(int rank, int world, int64_t max_groups, lq_p2p_t** out, void* out_handle64);
+int lq_p2p_connect(lq_p2p_t* p, const void* handles64_all);
+int lq_fq_bwd_threshold_finish_p2p(lq_p2p_t* p, const double* local_stats, int64_t C, float penalty_threshold,
+                                   double n_per_group, float* ds, lq_stream_t stream);
+int lq_p2p_error(lq_p2p_t* p, int* out_flag);
+int lq_p2p_destroy(lq_p2p_t* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,11 @@ SIGNATURES = {
     "lq_opt_adam": (_I, [C.POINTER(OptDesc), _I, _F, _F, _F, _F, _I64, _P, _F, _P, _P]),
     "lq_opt_sgd": (_I, [C.POINTER(OptDesc), _I, _F, _F, _I, _F, _P, _P]),
     "lq_debug_divcheck": (_I, [_P, _I64, C.c_uint32, _P, _P]),
+    "lq_p2p_create": (_I, [_I, _I, _I64, C.POINTER(_P), _P]),
+    "lq_p2p_connect": (_I, [_P, _P]),
+    "lq_fq_bwd_threshold_finish_p2p": (_I, [_P, _P, _I64, _F, C.c_double, _P, _P]),
+    "lq_p2p_error": (_I, [_P, C.POINTER(_I)]),
+    "lq_p2p_destroy": (_I, [_P]),
     "lq_dp_unique_id": (_I, [_P]),
     "lq_dp_init": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "lq_dp_allreduce": (_I, [_P, _P, _I64, _F, _P]),

@@ -8,4 +8,4 @@
 The reference has no counterpart for dp.py / step.py: it is a single-device Keras `model.fit`
 (IMAGENETTE/nested_quantization_layer/experiment.py:774-788).
 """
-from .dp import Comm, NcclComm, TorchDistComm, GradBucket, exchange_gradients  # noqa: F401
+from .dp import Comm, NcclComm, P2PFinish, TorchDistComm, GradBucket, exchange_gradients  # noqa: F401

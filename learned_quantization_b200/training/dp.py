@@ -86,6 +86,42 @@ class NcclComm(Comm):
             self._h = C.c_void_p()
 
 
+class P2PFinish:
+    """lq_p2p_* (include/lq.h): exchange + finish of the sharded threshold backward fused into one kernel
+    over NVLink peer memory.  The 64-byte IPC handles are gathered through torch.distributed."""
+
+    def __init__(self, max_groups: int, rank: Optional[int] = None, world: Optional[int] = None):
+        import torch.distributed as dist
+        if rank is None:
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self.rank, self.world = int(rank), int(world)
+        self._h = C.c_void_p()
+        mine = C.create_string_buffer(64)
+        check(lib.lq_p2p_create(self.rank, self.world, int(max_groups), C.byref(self._h), mine))
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw))
+            check(lib.lq_p2p_connect(self._h, b"".join(handles)))
+
+    def finish(self, local_stats: torch.Tensor, penalty_threshold: float, n_per_group: float, ds: torch.Tensor) -> torch.Tensor:
+        if local_stats.dtype != torch.float64 or not local_stats.is_cuda or not local_stats.is_contiguous():
+            raise ValueError("local_stats must be a contiguous float64 CUDA tensor [C, 3]")
+        check(lib.lq_fq_bwd_threshold_finish_p2p(self._h, local_stats.data_ptr(), local_stats.shape[0],
+                                                 float(penalty_threshold), float(n_per_group), ds.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream))
+        return ds
+
+    def timed_out(self) -> bool:
+        flag = C.c_int(0)
+        check(lib.lq_p2p_error(self._h, C.byref(flag)))
+        return bool(flag.value)
+
+    def close(self):
+        if self._h:
+            check(lib.lq_p2p_destroy(self._h))
+            self._h = C.c_void_p()
+
+
 class TorchDistComm(Comm):
     """The same interface over a torch.distributed process group (gloo on CPU in the tests)."""
 

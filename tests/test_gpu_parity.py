@@ -297,6 +297,28 @@ def test_sharded_backward_equals_unsharded(lq, shape, s_shape, nshards):
         assert ds_close(host(ds), ds_ref.reshape(-1))
 
 
+def test_p2p_finish_world1_equals_plain_finish(lq):
+    """lq_fq_bwd_threshold_finish_p2p with a single rank: same kernel (push, flag, wait, fold), its own
+    memory as the only peer; must equal lq_fq_bwd_threshold_finish, epoch after epoch."""
+    from learned_quantization_b200.training.dp import P2PFinish
+    ops = lq.ops
+    rng = np.random.default_rng(33)
+    shape = (64, 300, 16)
+    P = rng.normal(0, 0.05, shape).astype(np.float32)
+    s = rng.uniform(5e-3, 2e-2, (1, 300, 1)).astype(np.float32)
+    p2p = P2PFinish(max_groups=512, rank=0, world=1)
+    try:
+        for it in range(5):
+            dy = rng.normal(0, 1e-3, shape).astype(np.float32)
+            _, st = ops.fq_bwd_threshold_stats(dev(dy), dev(P), dev(s), 1e-3, (64, 300, 16))
+            want = ops.fq_bwd_threshold_finish(st.unsqueeze(0).contiguous(), 1e-3, 64 * 16)
+            got = p2p.finish(st, 1e-3, 64 * 16, torch.empty(300, device="cuda"))
+            assert bits_equal(host(got), host(want)), it
+        assert not p2p.timed_out()
+    finally:
+        p2p.close()
+
+
 def test_unaligned_pointers_take_scalar_path(lq):
     ops = lq.ops
     rng = np.random.default_rng(5)
