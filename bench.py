@@ -294,19 +294,32 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # (1) the timed region: EXACTLY K steps between two events, nothing else on the stream
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    e_start.record()
     for i in range(args.steps):
         P, dy = sets[i % 2]
-        ev[i][0].record()
         fwd(P)
-        ev[i][1].record()
         bwd(P, dy)
-        ev[i][2].record()
+    e_end.record()
     barrier()
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    total_ms = e_start.elapsed_time(e_end)
+    # (2) per-kernel durations for the roofline: K launches of the forward between two events, then K
+    # launches of the backward (element kernel + second stage) between two events.  (An event record
+    # after every single kernel costs ~3 us of stream time per record and would be charged to the kernel.)
+    ef = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ef[0].record()
+    for i in range(args.steps):
+        fwd(sets[i % 2][0])
+    ef[1].record()
+    for i in range(args.steps):
+        bwd(*sets[i % 2])
+    ef[2].record()
+    barrier()
+    fwd_ms = ef[0].elapsed_time(ef[1]) / args.steps
+    bwd_ms = ef[1].elapsed_time(ef[2]) / args.steps
+    instr_ms = fwd_ms + bwd_ms
 
     # ---- end to end through the host-buffer C-ABI entry (pinned host arrays in, host arrays out)
     hP, hs, hdy = (torch.from_numpy(a).pin_memory() for a in (P_h, s_h, dy_h))
@@ -323,10 +336,10 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([total_ms, fwd_ms, bwd_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fwd_ms, bwd_ms, e2e_ms = t.tolist()
+    total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms = t.tolist()
     if rank == 0:
         step_ms = total_ms / args.steps
         value = (BYTES_FWD + BYTES_BWD) * n * world / (step_ms * 1e-3) / 1e9
@@ -347,6 +360,9 @@ def run_ours(args):
                           if p2p is not None else "lq_dp_allgather_f64")},
             "elements_per_s": n * world / (step_ms * 1e-3),
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "kernel_timing": "value / ms_per_step: K steps (fwd, bwd alternating) between two events; fwd_ms / bwd_ms / "
+                             "roofline: a second pass, K forward launches between two events, then K backward launches "
+                             "(element kernel + second stage) between two events",
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_kernel, 512 blocks)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

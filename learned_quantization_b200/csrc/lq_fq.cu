@@ -279,6 +279,55 @@ __device__ __forceinline__ void finalize_group(const FinJob& f, long long g) {
   }
 }
 
+// One WARP per group: the whole group's partials are in flight at once (4 independent 16-byte
+// loads per lane per trip, no shared memory, no block barrier) -- the block-per-group version above
+// spent most of its 5 us on two dependent load rounds and a 64-bit division per partial.
+// Lane l folds partials l, l+32, ... in that order, then a fixed shuffle tree: deterministic.
+__device__ __forceinline__ void finish_group_value(const FinJob& f, long long g, double sum, unsigned long long cnt, float mx) {
+  if (f.mode == FIN_STATS) {
+    double* st = reinterpret_cast<double*>(f.ds) + 3 * g;
+    st[0] = sum; st[1] = (double)cnt; st[2] = (double)mx;
+    return;
+  }
+  const double n_g = (double)f.outer * (double)f.inner;
+  const float mean = (cnt == 0ull) ? f.p1 : (float)(sum / n_g);
+  f.ds[g] = __fmul_rn(mean, mx);
+}
+
+__global__ void __launch_bounds__(256) finalize_warp_kernel(const __grid_constant__ FinJob f) {
+  cudaGridDependencySynchronize();
+  const long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= f.C) return;
+  const int lane = threadIdx.x & 31;
+  const long long K = partials_per_group(f);
+  double sum = 0.0;
+  unsigned long long cnt = 0ull;
+  float mx = 0.f;
+  const bool simple = (f.regime == REG_ROW && f.nseg == 1) || f.regime == REG_LIN || (f.regime == REG_COL && f.inner == 1);
+  // simple layouts: partial k of group g sits at base + k * stride
+  const long long stride = (f.regime == REG_ROW) ? f.C : (f.regime == REG_COL ? f.W : 1);
+  const float4* base = f.part + ((f.regime == REG_LIN) ? g * f.nlin : g);
+  for (long long k0 = lane; k0 < K; k0 += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long k = k0 + 32 * u;
+      v[u] = (k < K) ? (simple ? base[k * stride] : f.part[partial_index(f, g, k)]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sum += (double)v[u].x; cnt += (unsigned long long)__float_as_uint(v[u].y); mx = fmaxf(mx, v[u].z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) finish_group_value(f, g, sum, cnt, mx);
+}
+
 // Launched with programmatic stream serialisation (launch_after below): the grid may start
 // while the element kernel drains; griddepcontrol.wait holds it until that kernel has
 // completed and its partials are visible.
@@ -384,7 +433,7 @@ int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float
     if (rc) return rc;
     f.part = f.lin; f.regime = REG_LIN;
   }
-  return launch_after(finalize_kernel, dim3((unsigned)g.C), dim3(kFinThreads), st, "finalize launch", f);
+  return launch_after(finalize_warp_kernel, dim3((unsigned)((g.C + 7) / 8)), dim3(256), st, "finalize launch", f);
 }
 
 int check_blocks(const Geom& g) {

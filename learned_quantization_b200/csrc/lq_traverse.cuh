@@ -412,12 +412,14 @@ struct SmemPlan {
 template <class Op, bool STREAM, bool VEC>
 __global__ void __launch_bounds__(kThreads) row_kernel(const __grid_constant__ Job j, const Op op) {
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
+  cudaGridDependencySynchronize();   // launched with launch_after: ordering with the previous kernel is kept here
   run_row<Op, STREAM, VEC>(j, blockIdx.x, op, queue);
 }
 template <class Op, bool STREAM, bool VEC>
 __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ Job j, const Op op) {
   __shared__ Acc smem[SmemPlan<Op>::kColEntries];
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
+  cudaGridDependencySynchronize();
   run_col<Op, STREAM, VEC>(j, blockIdx.x, op, smem, queue);
 }
 
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ Jo
   }
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
   if (j.vec) run_job<Op, false, true>(j, blk, op, smem, queue);
   else run_job<Op, false, false>(j, blk, op, smem, queue);
 }
@@ -483,11 +486,11 @@ int launch_job(const Job& j, const Op& op, cudaStream_t st) {
 #define LQ_LAUNCH(KERNEL)                                                            \
   do {                                                                               \
     if (j.stream_hint) {                                                             \
-      if (j.vec) KERNEL<Op, true, true><<<grid, block, 0, st>>>(j, op);              \
-      else KERNEL<Op, true, false><<<grid, block, 0, st>>>(j, op);                   \
+      if (j.vec) return launch_after(KERNEL<Op, true, true>, grid, block, st, "kernel launch", j, op);   \
+      return launch_after(KERNEL<Op, true, false>, grid, block, st, "kernel launch", j, op);             \
     } else {                                                                         \
-      if (j.vec) KERNEL<Op, false, true><<<grid, block, 0, st>>>(j, op);             \
-      else KERNEL<Op, false, false><<<grid, block, 0, st>>>(j, op);                  \
+      if (j.vec) return launch_after(KERNEL<Op, false, true>, grid, block, st, "kernel launch", j, op);  \
+      return launch_after(KERNEL<Op, false, false>, grid, block, st, "kernel launch", j, op);            \
     }                                                                                \
   } while (0)
   if (j.regime == REG_ROW) LQ_LAUNCH(row_kernel); else LQ_LAUNCH(col_kernel);
@@ -500,8 +503,7 @@ int launch_mt(JobTable& tab, const Op& op, cudaStream_t st) {
   unsigned total = 0;
   for (int i = 0; i < tab.n; ++i) { tab.job[i].block_begin = total; total += tab.job[i].nblocks; }
   if (total == 0) return LQ_OK;
-  mt_kernel<Op><<<dim3(total), dim3(kThreads), 0, st>>>(tab, op);
-  return cuda_fail(cudaGetLastError(), "multi-tensor kernel launch");
+  return launch_after(mt_kernel<Op>, dim3(total), dim3(kThreads), st, "multi-tensor kernel launch", tab, op);
 }
 
 }  // namespace lq
