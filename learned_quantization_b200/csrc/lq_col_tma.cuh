@@ -116,12 +116,12 @@ __global__ void __launch_bounds__(kThreads) col_tma_kernel(const __grid_constant
   }
 
   const long long grp = col_ok ? (col0 + c) / j.inner : 0;
-  const typename Op::Ctx ctx = op.prep(col_ok ? __ldg(j.s + grp) : 1.0f, make_float4(0.f, 0.f, 0.f, 0.f));
+  Job dummy{};
+  const typename Op::Ctx ctx = op.prep(col_ok ? __ldg(j.s + grp) : 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), dummy);
   Acc acc; Op::init(acc);
   Defer df;
   df.slot = sm.queue + warp * (kTmaRowsPerThread * 32) + lane;
   df.n = 0;
-  Job dummy{};
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int st = tile % kTmaStages;

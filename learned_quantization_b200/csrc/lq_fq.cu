@@ -16,7 +16,7 @@ struct FwdOp : OpBase<FwdOp<EXT>> {
   static constexpr bool kIn2 = false, kOutIsY = true, kCodes = true, kReduce = false, kAux = false;
   __device__ static void init(Acc&) {}
   __device__ static void combine(Acc&, const Acc&) {}
-  __device__ __forceinline__ Recip prep(float s, const float4&) const { return make_recip(s); }
+  __device__ __forceinline__ Recip prep(float s, const float4&, const Job&) const { return make_recip(s); }
   __device__ __forceinline__ void elem(float p, float, const Recip& c, const Job&, Acc&, float& y, float& q) const {
     q = round_code<EXT>(div_by(p, c), qm);
     y = __fmul_rn(q, c.s);
@@ -85,7 +85,7 @@ struct BwdThresholdOp : OpBase<BwdThresholdOp<EXT>> {
   static constexpr bool kIn2 = true, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; x.b += y.b; x.c = fmaxf(x.c, y.c); }
-  __device__ __forceinline__ Recip prep(float s, const float4&) const {
+  __device__ __forceinline__ Recip prep(float s, const float4&, const Job&) const {
     Recip r = make_recip(s);
     r.fast = r.fast && lam_fast;
     return r;

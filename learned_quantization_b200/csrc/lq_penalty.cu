@@ -8,69 +8,136 @@
 namespace lq {
 
 // --------------------------------------------------------------- element operators
+// All quotients by the group's scale go through the hoisted reciprocal (div_by / div_fast,
+// lq_common.cuh): the same IEEE results as __fdiv_rn at a third of the instructions.  Quotients whose
+// dividend is a per-group constant (the incoming gradient) are computed once in prep().
+struct PenCtx { Recip rc; float4 aux; float k0, k1, k2; };
+
+__device__ __forceinline__ float sgn(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+
 // MaxBin forward: per group max_j(|P_j| / s) and how many elements attain it (the tie
 // count _MinOrMaxGrad divides by).  acc.c = max, acc.b = ties.
 struct MaxBinStatOp : OpBase<MaxBinStatOp> {
+  using Ctx = PenCtx;
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = -1.f; }
   __device__ static void combine(Acc& x, const Acc& y) {
     if (y.c > x.c) { x.c = y.c; x.b = y.b; }
     else if (y.c == x.c) x.b += y.b;
   }
-  __device__ __forceinline__ void elem(float p, float, const PlainCtx& c, const Job&, Acc& acc, float&, float&) const {
-    const float s = c.s;
-    const float d = __fdiv_rn(fabsf(p), s);          // LF:92 tf.abs(kernel) / kernel_scale
-    if (d > acc.c) { acc.c = d; acc.b = 1u; }
-    else if (d == acc.c) acc.b += 1u;
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const { return PenCtx{make_recip(s), aux, 0.f, 0.f, 0.f}; }
+  // branch-free (a thread sees only 16 elements per unit, so "is this a new maximum" is true far too
+  // often for a branch: the branchy version ran with 24 of 32 lanes live); a NaN quotient is ignored
+  // exactly as by the comparisons of combine()
+  __device__ __forceinline__ void take(float d, Acc& acc) const {
+    const unsigned eq = (d == acc.c) ? 1u : 0u;
+    acc.b = (d > acc.c) ? 1u : acc.b + eq;
+    acc.c = fmaxf(acc.c, d);
+  }
+  __device__ __forceinline__ void elem(float p, float, const PenCtx& c, const Job&, Acc& acc, float&, float&) const {
+    take(div_by(fabsf(p), c.rc), acc);                 // LF:92 tf.abs(kernel) / kernel_scale
+  }
+  __device__ __forceinline__ void quad(const float4& p, const float4&, const PenCtx& c, const Job&, Acc& acc,
+                                       float4&, float4&, Defer&) const {
+    float4 d;
+    if (c.rc.fast && fast_range4(p)) {
+      d.x = div_fast(fabsf(p.x), c.rc); d.y = div_fast(fabsf(p.y), c.rc);
+      d.z = div_fast(fabsf(p.z), c.rc); d.w = div_fast(fabsf(p.w), c.rc);
+    } else {
+      d.x = __fdiv_rn(fabsf(p.x), c.rc.s); d.y = __fdiv_rn(fabsf(p.y), c.rc.s);
+      d.z = __fdiv_rn(fabsf(p.z), c.rc.s); d.w = __fdiv_rn(fabsf(p.w), c.rc.s);
+    }
+    take(d.x, acc); take(d.y, acc); take(d.z, acc); take(d.w, acc);
   }
 };
 
 // Difference forward: sum_j |P_j - P_j / s|  (LF:175-178, un-floored quotient). acc.a = sum.
 struct DiffStatOp : OpBase<DiffStatOp> {
+  using Ctx = PenCtx;
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
-  __device__ __forceinline__ void elem(float p, float, const PlainCtx& c, const Job&, Acc& acc, float&, float&) const {
-    const float s = c.s;
-    acc.a += fabsf(__fsub_rn(p, __fdiv_rn(p, s)));
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const { return PenCtx{make_recip(s), aux, 0.f, 0.f, 0.f}; }
+  __device__ __forceinline__ void elem(float p, float, const PenCtx& c, const Job&, Acc& acc, float&, float&) const {
+    acc.a += fabsf(__fsub_rn(p, div_by(p, c.rc)));
+  }
+  __device__ __forceinline__ void quad(const float4& p, const float4&, const PenCtx& c, const Job&, Acc& acc,
+                                       float4&, float4&, Defer&) const {
+    if (c.rc.fast && fast_range4(p)) {
+      acc.a += fabsf(__fsub_rn(p.x, div_fast(p.x, c.rc))); acc.a += fabsf(__fsub_rn(p.y, div_fast(p.y, c.rc)));
+      acc.a += fabsf(__fsub_rn(p.z, div_fast(p.z, c.rc))); acc.a += fabsf(__fsub_rn(p.w, div_fast(p.w, c.rc)));
+    } else {
+      acc.a += fabsf(__fsub_rn(p.x, __fdiv_rn(p.x, c.rc.s))); acc.a += fabsf(__fsub_rn(p.y, __fdiv_rn(p.y, c.rc.s)));
+      acc.a += fabsf(__fsub_rn(p.z, __fdiv_rn(p.z, c.rc.s))); acc.a += fabsf(__fsub_rn(p.w, __fdiv_rn(p.w, c.rc.s)));
+    }
   }
 };
 
-__device__ __forceinline__ float sgn(float x) { return (float)((x > 0.f) - (x < 0.f)); }
-
 // MaxBin backward w.r.t. P: aux = {mb_g, ties, coef_g = (1/ties) * g_mb}.
 //   g_d = indicator(d == mb) * coef ; g_a = g_d / s ; g_P = g_a * sign(P)
+// g_d takes two values per group, so both quotients g_d / s are prepared once: k0 = coef / s, k1 = 0 / s.
 template <bool ACCUM>
 struct MaxBinBwdOp : OpBase<MaxBinBwdOp<ACCUM>> {
+  using Ctx = PenCtx;
   const float* up;   // effective upstream (device scalar); already folded into aux.z
   static constexpr bool kIn2 = ACCUM, kOutIsY = false, kCodes = false, kReduce = false, kAux = true;
   __device__ static void init(Acc&) {}
   __device__ static void combine(Acc&, const Acc&) {}
-  __device__ __forceinline__ void elem(float p, float old, const PlainCtx& c, const Job&, Acc&, float& dx, float&) const {
-    const float s = c.s;
-    const float4& aux = c.aux;
-    const float d = __fdiv_rn(fabsf(p), s);
-    const float g_d = (d == aux.x) ? aux.z : 0.f;
-    const float g = __fmul_rn(__fdiv_rn(g_d, s), sgn(p));
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const {
+    return PenCtx{make_recip(s), aux, __fdiv_rn(aux.z, s), __fdiv_rn(0.0f, s), 0.f};
+  }
+  __device__ __forceinline__ void elem(float p, float old, const PenCtx& c, const Job&, Acc&, float& dx, float&) const {
+    const float d = div_by(fabsf(p), c.rc);
+    const float g = __fmul_rn((d == c.aux.x) ? c.k0 : c.k1, sgn(p));
     dx = ACCUM ? __fadd_rn(old, g) : g;
   }
 };
 
 // Difference backward: d = P - P/s ; g_d = g_abs * sign(d)
-//   g_P = g_d + (-g_d)/s ;  ds_g += (-g_d) * ((-P / s) / s)      (job.t0 = g_abs)
+//   g_P = g_d + (-g_d)/s ;  ds_g += (-g_d) * ((-P / s) / s)
+// With g_abs = t0 * upstream constant per tensor: g_P = sign(d) * (g_abs + (-g_abs)/s) exactly (RN is
+// symmetric under negation), prepared once per group as k1; k0 = g_abs.
 template <bool ACCUM>
 struct DiffBwdOp : OpBase<DiffBwdOp<ACCUM>> {
+  using Ctx = PenCtx;
   const float* up;   // effective upstream (device scalar)
   static constexpr bool kIn2 = ACCUM, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
-  __device__ __forceinline__ void elem(float p, float old, const PlainCtx& c, const Job& j, Acc& acc, float& dx, float&) const {
-    const float s = c.s;
-    const float pq = __fdiv_rn(p, s);
-    const float g_d = __fmul_rn(__fmul_rn(j.t0, __ldg(up)), sgn(__fsub_rn(p, pq)));
-    const float g = __fadd_rn(g_d, __fdiv_rn(-g_d, s));
-    acc.a += __fmul_rn(-g_d, __fdiv_rn(-pq, s));
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job& j) const {
+    const float gabs = __fmul_rn(j.t0, __ldg(up));
+    return PenCtx{make_recip(s), aux, gabs, __fadd_rn(gabs, __fdiv_rn(-gabs, s)), 0.f};
+  }
+  __device__ __forceinline__ void elem(float p, float old, const PenCtx& c, const Job&, Acc& acc, float& dx, float&) const {
+    const float pq = div_by(p, c.rc);
+    const float sg = sgn(__fsub_rn(p, pq));
+    const float g = __fmul_rn(sg, c.k1);
+    acc.a += __fmul_rn(__fmul_rn(-sg, c.k0), div_by(-pq, c.rc));
     dx = ACCUM ? __fadd_rn(old, g) : g;
+  }
+  __device__ __forceinline__ void one_fast(float p, float old, const PenCtx& c, Acc& acc, float& dx) const {
+    const float pq = div_fast(p, c.rc);
+    const float sg = sgn(__fsub_rn(p, pq));
+    acc.a += __fmul_rn(__fmul_rn(-sg, c.k0), div_fast(-pq, c.rc));
+    const float g = __fmul_rn(sg, c.k1);
+    dx = ACCUM ? __fadd_rn(old, g) : g;
+  }
+  __device__ __forceinline__ void quad(const float4& p, const float4& old, const PenCtx& c, const Job& j, Acc& acc,
+                                       float4& dx, float4& q, Defer&) const {
+    // both dividends inside the window: |p| in [2^-80, 2^80] and, with |s| in [2^-40, 2^40], |p / s| in
+    // [2^-120, 2^120] -- the second quotient is checked on its own dividend
+    bool fast = c.rc.fast && fast_range4(p);
+    if (fast) {
+      const float4 pq = make_float4(div_fast(p.x, c.rc), div_fast(p.y, c.rc), div_fast(p.z, c.rc), div_fast(p.w, c.rc));
+      fast = fast_range4(pq);
+    }
+    if (fast) {
+      one_fast(p.x, old.x, c, acc, dx.x); one_fast(p.y, old.y, c, acc, dx.y);
+      one_fast(p.z, old.z, c, acc, dx.z); one_fast(p.w, old.w, c, acc, dx.w);
+    } else {
+      elem(p.x, old.x, c, j, acc, dx.x, q.x); elem(p.y, old.y, c, j, acc, dx.y, q.y);
+      elem(p.z, old.z, c, j, acc, dx.z, q.z); elem(p.w, old.w, c, j, acc, dx.w, q.w);
+    }
   }
 };
 
@@ -79,8 +146,55 @@ template <class Op> static Op make_pen_op(const float* up) { Op op; op.up = up; 
 // --------------------------------------------------------------- second stages
 enum { PFIN_MAXBIN = 1, PFIN_SUM = 2, PFIN_SUM_DS = 3 };
 
+// Intermediate level for groups with very many partials (a per-tensor scale on a large tensor):
+// block (g, m) folds partials [m*kFinChunk, (m+1)*kFinChunk) of group g -- sum, and max with its tie
+// count -- into lin[g*nlin + m]; the last level then reads REG_LIN partials.  Fixed order.
+__global__ void __launch_bounds__(256) pen_fold_kernel(const __grid_constant__ FinJob f) {
+  cudaGridDependencySynchronize();
+  const long long g = blockIdx.x / f.nlin, m = blockIdx.x - g * f.nlin;
+  const long long K = partials_per_group(f);
+  const long long k0 = m * kFinChunk;
+  double sum = 0.0;
+  float mx = -1.f;
+  unsigned long long ties = 0ull;
+  float4 v[kFinChunk / 256];
+#pragma unroll
+  for (int u = 0; u < kFinChunk / 256; ++u) {
+    const long long k = k0 + u * 256 + threadIdx.x;
+    v[u] = (k < K) ? f.part[partial_index(f, g, k)] : make_float4(0.f, 0.f, -2.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < kFinChunk / 256; ++u) {
+    sum += (double)v[u].x;
+    const unsigned long long b = __float_as_uint(v[u].y);
+    if (v[u].z > mx) { mx = v[u].z; ties = b; } else if (v[u].z == mx) ties += b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const unsigned long long ot = __shfl_xor_sync(0xffffffffu, ties, o);
+    if (omx > mx) { mx = omx; ties = ot; } else if (omx == mx) ties += ot;
+  }
+  __shared__ double ssum[8];
+  __shared__ unsigned long long sties[8];
+  __shared__ float smx[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; sties[w] = ties; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = ssum[0]; ties = sties[0]; mx = smx[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      sum += ssum[i];
+      if (smx[i] > mx) { mx = smx[i]; ties = sties[i]; } else if (smx[i] == mx) ties += sties[i];
+    }
+    f.lin[blockIdx.x] = make_float4((float)sum, __uint_as_float((unsigned)(ties > 0xffffffffull ? 0xffffffffull : ties)), mx, 0.f);
+  }
+}
+
 __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g) {
-  const long long K = (f.regime == REG_ROW) ? f.outer * f.nseg : f.nchunks * f.inner;
+  const long long K = partials_per_group(f);
   double sum = 0.0;
   float mx = -1.f;
   unsigned long long ties = 0ull;
@@ -129,6 +243,7 @@ __global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_
     if (tab.job[mid].group_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
   }
   const FinJob& f = tab.job[lo];
+  cudaGridDependencySynchronize();
   pen_finalize_group(f, blockIdx.x - f.group_begin);
 }
 
@@ -141,15 +256,17 @@ __device__ __forceinline__ double gstat_double(const float4& v) {
   return __longlong_as_double((long long)bits);
 }
 
+// Warp w takes tensors w, w+8, ...: the per-tensor term needs one warp reduction, the terms are then
+// added in tensor order by one thread (a single block used to walk the tensors one after the other
+// with two block barriers each: 30 us for the 40 tensors of the IMAGENETTE model).
 __global__ void __launch_bounds__(256) pen_scalar_kernel(const __grid_constant__ ScalarTable tab, double* total, float* out) {
-  __shared__ double red[256 / 32];
-  __shared__ double acc;
-  if (threadIdx.x == 0) acc = tab.first ? 0.0 : *total;
-  __syncthreads();
-  for (int t = 0; t < tab.n; ++t) {
+  cudaGridDependencySynchronize();
+  __shared__ double term[kMaxMT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < tab.n; t += 8) {
     const ScalarJob& j = tab.job[t];
     double v = 0.0;
-    for (long long g = threadIdx.x; g < j.C; g += 256) {
+    for (long long g = lane; g < j.C; g += 32) {
       if (tab.kind == LQ_PEN_MAXBIN) v += (double)j.gstat[g].x;
       else if (tab.kind == LQ_PEN_DIFFERENCE) v += gstat_double(j.gstat[g]);
       else {
@@ -160,19 +277,17 @@ __global__ void __launch_bounds__(256) pen_scalar_kernel(const __grid_constant__
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int i = 0; i < 256 / 32; ++i) s += red[i];
+    if (lane == 0) {
       // mean over groups (MaxBin LF:110, Inverse LF:258) or over elements (Difference LF:178), times #P
       const double denom = (tab.kind == LQ_PEN_DIFFERENCE) ? j.n : (double)j.C;
-      const float mean = (float)(s / denom);
-      acc += (double)__fmul_rn(mean, (float)j.n);
+      const float mean = (float)(v / denom);
+      term[t] = (double)__fmul_rn(mean, (float)j.n);
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    double acc = tab.first ? 0.0 : *total;
+    for (int t = 0; t < tab.n; ++t) acc += term[t];
     *total = acc;
     if (tab.last) *out = (float)(acc / tab.normalizer);
   }
@@ -188,6 +303,7 @@ __global__ void upstream_kernel(float* dst, float host_val, const float* dev_val
 }
 
 __global__ void __launch_bounds__(128) pen_group_kernel(const __grid_constant__ GroupTable tab, const float* up) {
+  cudaGridDependencySynchronize();
   const unsigned gid = blockIdx.x * 128u + threadIdx.x;
   if (gid >= tab.total) return;
   int lo = 0, hi = tab.n - 1;
@@ -216,6 +332,20 @@ __global__ void __launch_bounds__(128) pen_group_kernel(const __grid_constant__ 
 }
 
 // --------------------------------------------------------------- host side
+// Tensors whose groups have more than kFinSplit partials get the intermediate fold; their entry in
+// the finalize table then points at the folded partials.
+static int pen_fold_large(FinTable& fin, cudaStream_t st) {
+  for (int i = 0; i < fin.n; ++i) {
+    FinJob& f = fin.job[i];
+    if (f.nlin <= 0 || f.regime == REG_LIN) continue;
+    if (f.C * f.nlin > 0x7fffffffll) { set_error("too many intermediate partials"); return LQ_E_BADSHAPE; }
+    int rc = launch_after(pen_fold_kernel, dim3((unsigned)(f.C * f.nlin)), dim3(256), st, "penalty fold launch", f);
+    if (rc) return rc;
+    f.part = f.lin; f.regime = REG_LIN;
+  }
+  return LQ_OK;
+}
+
 struct PenLayout { size_t part_off, gstat_off; };
 
 static size_t pen_slots(const lq_tensor_desc& d) {
@@ -295,6 +425,7 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
         f.part = part; f.gstat = gstat; f.s = d.s; f.ds = nullptr;
         f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
         f.regime = g.regime; f.mode = (kind == LQ_PEN_MAXBIN) ? PFIN_MAXBIN : PFIN_SUM;
+        f.nlin = g.nlin; f.lin = part + g.npart1;
         f.group_begin = groups; groups += (unsigned)d.C;
         fin.job[fin.n++] = f;
       }
@@ -305,11 +436,10 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
       if (kind == LQ_PEN_MAXBIN) rc = launch_mt(tab, MaxBinStatOp{}, st);
       else rc = launch_mt(tab, DiffStatOp{}, st);
       if (rc) break;
-      pen_finalize_kernel<<<dim3(groups), dim3(kFinThreads), 0, st>>>(fin);
-      if ((rc = cuda_fail(cudaGetLastError(), "penalty finalize launch"))) break;
+      if ((rc = pen_fold_large(fin, st))) break;
+      if ((rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty finalize launch", fin))) break;
     }
-    pen_scalar_kernel<<<1, 256, 0, st>>>(sc, total, out_penalty);
-    rc = cuda_fail(cudaGetLastError(), "penalty scalar launch");
+    rc = launch_after(pen_scalar_kernel, dim3(1), dim3(256), st, "penalty scalar launch", sc, total, out_penalty);
   }
   delete[] lay;
   return rc;
@@ -367,6 +497,7 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
           f.part = part; f.gstat = gstat; f.s = d.s; f.ds = d.ds;
           f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
           f.regime = g.regime; f.mode = PFIN_SUM_DS; f.flags = d.flags;
+          f.nlin = g.nlin; f.lin = part + g.npart1;
           f.group_begin = groups;
           fin.job[fin.n++] = f;
         }
@@ -376,16 +507,15 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
     if (rc) break;
     if (gt.n) {
       gt.total = groups;
-      pen_group_kernel<<<dim3((groups + 127) / 128), dim3(128), 0, st>>>(gt, up);
-      if ((rc = cuda_fail(cudaGetLastError(), "penalty group launch"))) break;
+      if ((rc = launch_after(pen_group_kernel, dim3((groups + 127) / 128), dim3(128), st, "penalty group launch", gt, up))) break;
     }
     if (tab.n) {
       if (kind == LQ_PEN_MAXBIN) rc = accum ? launch_mt(tab, make_pen_op<MaxBinBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<MaxBinBwdOp<false>>(up), st);
       else rc = accum ? launch_mt(tab, make_pen_op<DiffBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<DiffBwdOp<false>>(up), st);
       if (rc) break;
       if (fin.n) {
-        pen_finalize_kernel<<<dim3(groups), dim3(kFinThreads), 0, st>>>(fin);
-        rc = cuda_fail(cudaGetLastError(), "penalty ds finalize launch");
+        if ((rc = pen_fold_large(fin, st))) break;
+        rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty ds finalize launch", fin);
       }
     }
   }

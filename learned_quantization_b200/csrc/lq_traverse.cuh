@@ -6,7 +6,7 @@
 //   static constexpr bool kCodes    out1 is the integer code, written to Job::codes if set
 //   static constexpr bool kReduce   per-unit partials are produced
 //   static constexpr bool kAux      per-group float4 Job::gaux[g] is fetched next to the scale
-//   Ctx prep(s, aux)                 per-(thread, group) constants, hoisted out of the element loop
+//   Ctx prep(s, aux, job)            per-(thread, group) constants, hoisted out of the element loop
 //   elem(p, in2, ctx, job, acc, out0, out1)
 //   quad(p4, in2_4, ctx, job, acc, out0_4, out1_4, defer)   four consecutive elements of one
 //                                    group (ROW, 128-bit path); OpBase supplies it as 4 x elem
@@ -39,7 +39,7 @@ template <class D>
 struct OpBase {
   using Ctx = PlainCtx;
   static constexpr int kDeferSlots = 0;
-  __device__ __forceinline__ PlainCtx prep(float s, const float4& aux) const { return PlainCtx{s, aux}; }
+  __device__ __forceinline__ PlainCtx prep(float s, const float4& aux, const Job&) const { return PlainCtx{s, aux}; }
   __device__ __forceinline__ void flush(Acc&, Defer&) const {}
   // COL traversal: element of the thread's k-th column (its own group context and accumulator)
   template <class C>
@@ -97,7 +97,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
     grp = row % j.C;
   }
   const typename Op::Ctx ctx = op.prep(__ldg(j.s + grp),
-                                       Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
+                                       Op::kAux ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f), j);
   const long long base = row * j.inner + (long long)sg * j.seg;
   const long long rem = j.inner - (long long)sg * j.seg;
   const int len = rem < j.seg ? (int)rem : j.seg;
@@ -196,7 +196,7 @@ __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& o
 
   const long long grp = active ? col / j.inner : 0;
   const typename Op::Ctx ctx = op.prep(active ? __ldg(j.s + grp) : 1.0f,
-                                       (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
+                                       (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f), j);
   Acc acc; Op::init(acc);
   float* out = Op::kOutIsY ? j.y : j.dX;
   const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
@@ -297,7 +297,7 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
     Op::init(acc[k]);
     const long long grp = active ? (col0 + k) / j.inner : 0;
     ctx[k] = op.prep(active ? __ldg(j.s + grp) : 1.0f,
-                     (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f));
+                     (Op::kAux && active) ? __ldg(j.gaux + grp) : make_float4(0.f, 0.f, 0.f, 0.f), j);
   }
   float* out = Op::kOutIsY ? j.y : j.dX;
   const bool wr = Op::kOutIsY ? true : (j.write_dx != 0);
