@@ -18,8 +18,14 @@
 
 namespace lq {
 
-constexpr int kSlots = 3;
-constexpr long long kChunkElems = 4ll << 20;   // 16 MiB per staged array
+#ifndef LQ_HOST_SLOTS
+#define LQ_HOST_SLOTS 3
+#endif
+#ifndef LQ_HOST_CHUNK_ELEMS
+#define LQ_HOST_CHUNK_ELEMS (4ll << 20)          // 16 MiB per staged array
+#endif
+constexpr int kSlots = LQ_HOST_SLOTS;
+constexpr long long kChunkElems = LQ_HOST_CHUNK_ELEMS;
 
 struct HostPlan {
   int mode;                 // 0 outer, 1 groups, 2 segments
