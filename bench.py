@@ -419,12 +419,27 @@ def run_qat(args, rank, world, local):
     torch.backends.cudnn.benchmark = True
     batch, shape = args.qat_batch, (224, 224, 3)
     torch.manual_seed(42)
-    net = models.imagenette_resnet(1e-11, seed=42, orientation="channelwise", variant="nested").cuda().train()
+    variant = args.qat_variant
+    value = 1e-11 if variant == "nested" else 1e-9       # lambda (nested) / gamma (custom loss), chapter4.tex
+    net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant).cuda().train()
     x, y = models.synthetic_batch(batch, shape, "cuda", seed=42 + rank)
     with torch.no_grad():
         net(x[:2])                                    # builds the layers
     comm = NcclComm() if world > 1 else None
-    step = TrainStep(net, scce, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
+    loss_fn = scce
+    if variant == "custom_loss":                      # IMAGENETTE/custom_loss_terms/experiment.py:764-793
+        import tempfile
+        from learned_quantization_b200.custom_loss_terms.custom_components import custom_loss_functions as lf
+        from learned_quantization_b200.training.step import quantised_pairs
+        hosts = []
+        for h, _, _, _ in quantised_pairs(net):
+            if h not in hosts:
+                hosts.append(h)
+        cls = {"maxbin": lf.SCCEMaxBin, "difference": lf.SCCEDifference, "inverse": lf.SCCEInverse}[args.qat_loss]
+        loss_obj = cls(layers=hosts, penalty_rate=value, log_dir=tempfile.mkdtemp(prefix="lq_bench_"))
+        loss_obj.log_to_files = False                 # the reference's three tf.print(file://) per step: not timed here
+        loss_fn = loss_obj.compute_total_loss
+    step = TrainStep(net, loss_fn, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
     hx = x.cpu().pin_memory()
     hy = y.cpu().pin_memory()
 
@@ -468,8 +483,10 @@ def run_qat(args, rank, world, local):
            "ms_per_step": dev_ms, "steps": steps, "warmup": warm,
            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
-           "config": {"workload": "imagenette_resnet_nested_channelwise_224", "per_gpu_batch": batch, "global_batch": batch * world,
-                      "optimizer": "adam(1e-4) fused with l2 + MinValueConstraint", "lambda": 1e-11,
+           "config": {"workload": f"imagenette_resnet_{variant}_channelwise_224" + (f"_{args.qat_loss}" if variant == "custom_loss" else ""),
+                      "per_gpu_batch": batch, "global_batch": batch * world,
+                      "optimizer": "adam(1e-4) fused with l2 + MinValueConstraint",
+                      ("lambda" if variant == "nested" else "gamma"): value,
                       "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
                       "scale_grad_mode": "exact (allreduce dy, then threshold backward on every rank)",
                       "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}",
@@ -595,6 +612,8 @@ def main():
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)
+    ap.add_argument("--qat-variant", default="nested", choices=["nested", "custom_loss"])
+    ap.add_argument("--qat-loss", default="maxbin", choices=["maxbin", "difference", "inverse"])
     ap.add_argument("--qat-eager", action="store_true", help="do not capture the QAT step in a CUDA graph")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the shards' statistics are exchanged (fused peer-memory kernel, or NCCL all-gather)")

@@ -136,40 +136,6 @@ struct BwdThresholdOp : OpBase<BwdThresholdOp<EXT>> {
     }
     df.n = 0;
   }
-  // COL traversal: a thread's queue mixes its (up to four) columns, i.e. groups; the column
-  // index travels in the two sign bits the division does not use (|dy| and |nz|).
-  __device__ __forceinline__ void elem_k(float p, float dy, const Recip& c, const Job&, Acc* acc, int k,
-                                         float& dx, float&, Defer& df) const {
-    dx = dy;
-    if (c.fast && fast_range(p)) {
-      const float q = round_code<EXT>(div_fast(p, c), qm);
-      const float y = __fmul_rn(q, c.s);
-      const float nz = (y == 0.0f) ? kEps : y;
-      acc[k].c = fmaxf(acc[k].c, fabsf(q));
-      if (!(fabsf(dy) >= __fmul_rn(fabsf(nz), lam_hi))) {
-        df.slot[df.n * 32] = make_float2(__uint_as_float((__float_as_uint(dy) & 0x7fffffffu) | ((unsigned)(k & 1) << 31)),
-                                         __uint_as_float((__float_as_uint(nz) & 0x7fffffffu) | ((unsigned)(k >> 1) << 31)));
-        ++df.n;
-      }
-    } else {
-      slow(p, dy, c.s, acc[k]);
-    }
-  }
-  __device__ __forceinline__ void flush_k(Acc* acc, Defer& df) const {
-    const int m = __reduce_max_sync(0xffffffffu, df.n);
-    for (int i = 0; i < m; ++i) {
-      if (i < df.n) {
-        const float2 e = df.slot[i * 32];
-        const int k = (int)(__float_as_uint(e.x) >> 31) | ((int)(__float_as_uint(e.y) >> 31) << 1);
-        Acc one; one.a = 0.f; one.b = 0u; one.c = 0.f;
-        below(__fdiv_rn(fabsf(e.x), fabsf(e.y)), one);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if (kk == k) { acc[kk].a += one.a; acc[kk].b += one.b; }
-      }
-    }
-    df.n = 0;
-  }
   __device__ __forceinline__ void quad(const float4& p, const float4& d, const Recip& c, const Job&, Acc& acc,
                                        float4& dx, float4&, Defer& df) const {
     if (c.fast && fast_range4(p)) {
@@ -326,14 +292,6 @@ __global__ void __launch_bounds__(256) finalize_warp_kernel(const __grid_constan
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
   if (lane == 0) finish_group_value(f, g, sum, cnt, mx);
-}
-
-// Launched with programmatic stream serialisation (launch_after below): the grid may start
-// while the element kernel drains; griddepcontrol.wait holds it until that kernel has
-// completed and its partials are visible.
-__global__ void __launch_bounds__(kFinThreads) finalize_kernel(const __grid_constant__ FinJob f) {
-  cudaGridDependencySynchronize();
-  finalize_group(f, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kFinThreads) mt_finalize_kernel(const __grid_constant__ FinTable tab) {

@@ -307,10 +307,10 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 
   // The row loop is block-uniform (every thread runs the same trips; rows past the end and
   // idle threads are predicated off), so the warp is converged at flush_k.
-  // Rows per trip: 4 for the light operators; 2 for two-input reducing operators (the threshold
-  // backward), whose per-thread state (4 columns x {scale, reciprocal, 3 accumulators}) would
-  // otherwise push the kernel past 64 registers and halve the resident warps -- ncu showed that
-  // variant latency-bound on dependent-issue stalls at 4 warps per scheduler.
+  // Rows per trip: 4 for the light operators; 2 for two-input reducing operators (the accumulating
+  // Difference backward), whose per-thread state for four groups would otherwise push the kernel past
+  // 64 registers and halve the resident warps.  (The threshold backward does not come here: it takes
+  // run_col1 or the TMA-staged kernel.)
   constexpr int U = (Op::kIn2 && Op::kReduce) ? 2 : 4;
   const long long step = j.by;
   auto load = [&](long long rb, float (&p)[U][V], float (&d)[U][V]) {
