@@ -85,6 +85,15 @@ struct BwdThresholdOp : OpBase<BwdThresholdOp<EXT>> {
   static constexpr bool kIn2 = true, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; x.b += y.b; x.c = fmaxf(x.c, y.c); }
+  // the count and the maximum (non-negative, never NaN: its bit pattern orders like the value) reduce
+  // with one REDUX each; only the float sum needs the shuffle tree
+  __device__ __forceinline__ Acc warp_reduce(const Acc& x) const {
+    Acc r;
+    r.a = warp_sum(x.a);
+    r.b = __reduce_add_sync(0xffffffffu, x.b);
+    r.c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x.c)));
+    return r;
+  }
   __device__ __forceinline__ Recip prep(float s, const float4&, const Job&) const {
     Recip r = make_recip(s);
     r.fast = r.fast && lam_fast;

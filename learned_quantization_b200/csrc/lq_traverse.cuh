@@ -29,6 +29,19 @@ __device__ __forceinline__ Acc unpack_acc(const float4& v) {
   Acc x; x.a = v.x; x.b = __float_as_uint(v.y); x.c = v.z; return x;
 }
 
+template <class Op>
+__device__ __forceinline__ Acc warp_reduce_acc(Acc x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Acc y;
+    y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
+    y.b = __shfl_xor_sync(0xffffffffu, x.b, o);
+    y.c = __shfl_xor_sync(0xffffffffu, x.c, o);
+    Op::combine(x, y);
+  }
+  return x;
+}
+
 // Default per-group context (scale + optional aux operands) and default quad.
 struct PlainCtx { float s; float4 aux; };
 // A thread's private rare-case queue: entry k lives at slot[k * 32] (lane-interleaved inside the
@@ -41,6 +54,9 @@ struct OpBase {
   static constexpr int kDeferSlots = 0;
   __device__ __forceinline__ PlainCtx prep(float s, const float4& aux, const Job&) const { return PlainCtx{s, aux}; }
   __device__ __forceinline__ void flush(Acc&, Defer&) const {}
+  // warp-level reduction of a unit's accumulator (fixed tree: deterministic); operators whose fields
+  // are plain sum / integer sum / max override it with single-instruction integer reductions
+  __device__ __forceinline__ Acc warp_reduce(const Acc& x) const { return warp_reduce_acc<D>(x); }
   // COL traversal: element of the thread's k-th column (its own group context and accumulator)
   template <class C>
   __device__ __forceinline__ void elem_k(float p, float d, const C& c, const Job& j, Acc* acc, int k,
@@ -59,18 +75,6 @@ struct OpBase {
   }
 };
 
-template <class Op>
-__device__ __forceinline__ Acc warp_reduce_acc(Acc x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Acc y;
-    y.a = __shfl_xor_sync(0xffffffffu, x.a, o);
-    y.b = __shfl_xor_sync(0xffffffffu, x.b, o);
-    y.c = __shfl_xor_sync(0xffffffffu, x.c, o);
-    Op::combine(x, y);
-  }
-  return x;
-}
 
 __device__ __forceinline__ void store_code(void* codes, int dtype, long long idx, float q) {
   if (dtype == LQ_CODES_F32) reinterpret_cast<float*>(codes)[idx] = q;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
     }
   }
   if (Op::kReduce) {
-    acc = warp_reduce_acc<Op>(acc);
+    acc = op.warp_reduce(acc);
     if (lane == 0) j.part[unit] = pack_acc(acc);
   }
 }
