@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) col_tma_kernel(const __grid_constant
 // Shape-only eligibility and geometry (pointer alignment is checked at launch).
 inline bool col_tma_shape_ok(long long outer, long long C, long long inner) {
   const long long W = C * inner;
-  return inner < kRowMinInner && (W % 4 == 0) && W >= 32 && outer >= 512 && outer * W >= (1ll << 20) &&
+  return C > 1 && inner < kRowMinInner && (W % 4 == 0) && W >= 32 && outer >= 512 && outer * W >= (1ll << 20) &&
          W < (1ll << 31) && outer < (1ll << 31);
 }
 inline Geom make_col_tma_geom(long long outer, long long C, long long inner) {

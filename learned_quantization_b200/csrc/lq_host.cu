@@ -80,6 +80,7 @@ extern "C" int lq_host_workspace_bytes(int64_t outer, int64_t C, int64_t inner, 
   int rc = check_dims(outer, C, inner);
   if (rc) return rc;
   if (outer * C * inner == 0) { *out_bytes = 0; return LQ_OK; }
+  if (C == 1) { inner *= outer; outer = 1; }
   *out_bytes = make_plan(outer, C, inner).total;
   return LQ_OK;
 }
@@ -93,6 +94,7 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
   const long long n = outer * C * inner;
   if (n == 0) return LQ_OK;
   if (!hP || !hs || !hdy || !hy || !hds) { set_error("lq_host_fq_fwd_bwd: null host array"); return LQ_E_NULLPTR; }
+  if (C == 1) { inner *= outer; outer = 1; }            // one group: a flat run (as make_geom does)
   const HostPlan p = make_plan(outer, C, inner);
   if (!dev_ws || dev_ws_bytes < p.total || !aligned16(dev_ws)) {
     set_error("lq_host_fq_fwd_bwd: device workspace %zu B needed, got %zu", p.total, dev_ws_bytes);

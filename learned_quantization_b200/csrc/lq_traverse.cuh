@@ -427,10 +427,12 @@ __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ J
   run_col<Op, STREAM, VEC>(j, blockIdx.x, op, smem, queue);
 }
 
-// Multi-tensor kernel: block -> tensor by binary search over block_begin.
-template <class Op>
+// Multi-tensor kernel: block -> tensor by binary search over block_begin.  One instantiation per
+// regime (a launch holds the ROW tensors or the COL tensors of a step, never both), so that the ROW
+// units keep the ROW kernel's register budget: the combined kernel needed 114 registers.
+template <class Op, int REGIME>
 __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
-  __shared__ Acc smem[SmemPlan<Op>::kColEntries];
+  __shared__ Acc smem[REGIME == REG_COL ? SmemPlan<Op>::kColEntries : 1];
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
@@ -440,8 +442,13 @@ __global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ Jo
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
   cudaGridDependencySynchronize();
-  if (j.vec) run_job<Op, false, true>(j, blk, op, smem, queue);
-  else run_job<Op, false, false>(j, blk, op, smem, queue);
+  if constexpr (REGIME == REG_ROW) {
+    if (j.vec) run_row<Op, false, true>(j, blk, op, queue);
+    else run_row<Op, false, false>(j, blk, op, queue);
+  } else {
+    if (j.vec) run_col<Op, false, true>(j, blk, op, smem, queue);
+    else run_col<Op, false, false>(j, blk, op, smem, queue);
+  }
 }
 
 constexpr int kFinThreads = 128;
@@ -504,10 +511,24 @@ int launch_job(const Job& j, const Op& op, cudaStream_t st) {
 
 template <class Op>
 int launch_mt(JobTable& tab, const Op& op, cudaStream_t st) {
-  unsigned total = 0;
-  for (int i = 0; i < tab.n; ++i) { tab.job[i].block_begin = total; total += tab.job[i].nblocks; }
-  if (total == 0) return LQ_OK;
-  return launch_after(mt_kernel<Op>, dim3(total), dim3(kThreads), st, "multi-tensor kernel launch", tab, op);
+  JobTable part;
+  for (int regime = REG_ROW; regime <= REG_COL; ++regime) {
+    part.n = 0;
+    unsigned total = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      if (tab.job[i].regime != regime || tab.job[i].nblocks == 0) continue;
+      part.job[part.n] = tab.job[i];
+      part.job[part.n].block_begin = total;
+      total += tab.job[i].nblocks;
+      ++part.n;
+    }
+    if (total == 0) continue;
+    const int rc = (regime == REG_ROW)
+        ? launch_after(mt_kernel<Op, REG_ROW>, dim3(total), dim3(kThreads), st, "multi-tensor ROW launch", part, op)
+        : launch_after(mt_kernel<Op, REG_COL>, dim3(total), dim3(kThreads), st, "multi-tensor COL launch", part, op);
+    if (rc) return rc;
+  }
+  return LQ_OK;
 }
 
 }  // namespace lq
