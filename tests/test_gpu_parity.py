@@ -435,6 +435,41 @@ def test_penalties_random_vs_oracle(lq):
             assert float(np.max(np.abs(host(dss[i]).astype(np.float64).reshape(gs.shape) - gs))) <= TOL * max(float(np.max(np.abs(gs))), 1e-30), (kind, i)
 
 
+def test_penalties_many_tensors_and_a_huge_group(lq):
+    """More tensors than one kernel-parameter table holds (the scalar stage chains over launches) and a
+    per-tensor scale on a 9.4 M-element kernel (more than 4096 partials: the two-level fold)."""
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(22)
+    specs = [((3, 3, 8, 16), (1, 1, 8, 1))] * 14 + [((40, 12), (40, 1))] * 14 + [((3, 3, 1024, 1024), (1,))]
+    layers = []
+    for sh, ssh in specs:
+        K = rng.normal(0, 0.05, size=sh).astype(np.float32)
+        sK = rng.uniform(5e-3, 2e-2, size=ssh).astype(np.float32)
+        b = rng.normal(0, 0.05, size=(sh[-1],)).astype(np.float32)
+        sb = rng.uniform(5e-3, 2e-2, size=(1,)).astype(np.float32)
+        layers.append((K, sK, b, sb))
+    K = layers[-1][0]
+    K.reshape(-1)[[5, 77777, 9_000_000]] = np.float32(0.9)          # a three-way tie for the global maximum
+    Ps, ss = [], []
+    for K, sK, b, sb in layers:
+        Ps += [dev(K), dev(b)]; ss += [dev(sK), dev(sb)]
+    assert len(Ps) == 58
+    for kind, val, grad in ((_lib.LQ_PEN_MAXBIN, o.maxbin_penalty, o.maxbin_penalty_grads),
+                            (_lib.LQ_PEN_DIFFERENCE, o.difference_penalty, o.difference_penalty_grads),
+                            (_lib.LQ_PEN_INVERSE, o.inverse_penalty, o.inverse_penalty_grads)):
+        out, ws = ops.penalty_fwd(kind, Ps, ss)
+        assert rel_err(host(out), val(layers)) < TOL, kind
+        dXs, dss = ops.penalty_bwd(kind, Ps, ss, ws, 2.0)
+        ref = grad(layers, 2.0, accum="fp64")
+        for i in (0, 1, 28, 29, 56, 57):                              # first, middle and the huge layer
+            gK, gsK, gb, gsb = ref[i // 2]
+            gP, gs = (gK, gsK) if i % 2 == 0 else (gb, gsb)
+            if kind != _lib.LQ_PEN_INVERSE:
+                assert float(np.max(np.abs(host(dXs[i]).astype(np.float64) - gP))) <= TOL * max(float(np.max(np.abs(gP))), 1e-30), (kind, i)
+            assert float(np.max(np.abs(host(dss[i]).astype(np.float64).reshape(gs.shape) - gs))) <= TOL * max(float(np.max(np.abs(gs))), 1e-30), (kind, i)
+
+
 def test_host_buffer_path_matches_device_path(lq):
     ops = lq.ops
     rng = np.random.default_rng(31)
