@@ -473,7 +473,8 @@ def test_penalties_many_tensors_and_a_huge_group(lq):
 def test_host_buffer_path_matches_device_path(lq):
     ops = lq.ops
     rng = np.random.default_rng(31)
-    for layout in [(64, 512, 512), (1, 1, 9_000_001), (1, 6, 3_000_000), (70000, 64, 1), (3, 5, 7)]:
+    for layout in [(64, 512, 512), (1, 1, 9_000_001), (1, 6, 3_000_000), (70000, 64, 1), (3, 5, 7), (300000, 1, 40),
+                   (40000, 16, 16), (9, 2_000_000, 1)]:
         n = layout[0] * layout[1] * layout[2]
         P = rng.normal(0, 0.05, size=n).astype(np.float32)
         dy = rng.normal(0, 1e-3, size=n).astype(np.float32)
