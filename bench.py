@@ -421,7 +421,8 @@ def run_qat(args, rank, world, local):
     torch.manual_seed(42)
     variant = args.qat_variant
     value = 1e-11 if variant == "nested" else 1e-9       # lambda (nested) / gamma (custom loss), chapter4.tex
-    net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant).cuda().train()
+    net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant,
+                                   kernel_storage=args.qat_storage).cuda().train()
     x, y = models.synthetic_batch(batch, shape, "cuda", seed=42 + rank)
     with torch.no_grad():
         net(x[:2])                                    # builds the layers
@@ -490,6 +491,8 @@ def run_qat(args, rank, world, local):
                       "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
                       "scale_grad_mode": "exact (allreduce dy, then threshold backward on every rank)",
                       "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}",
+                      "kernel_storage": args.qat_storage + (" (logical HWIO, cuDNN channels-last order in memory)"
+                                                            if args.qat_storage == "ohwi" else ""),
                       "launch": "eager" if args.qat_eager else "one CUDA graph per step"},
            "allreduce_floats": step.bucket.n_exact,
            "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 2, "lq_opt_adam": -(-len(step.table.params) // 56),
@@ -614,6 +617,8 @@ def main():
     ap.add_argument("--qat-warmup", type=int, default=5)
     ap.add_argument("--qat-variant", default="nested", choices=["nested", "custom_loss"])
     ap.add_argument("--qat-loss", default="maxbin", choices=["maxbin", "difference", "inverse"])
+    ap.add_argument("--qat-storage", default="ohwi", choices=["hwio", "ohwi"],
+                    help="memory order of the conv kernels (logical shape is HWIO either way)")
     ap.add_argument("--qat-eager", action="store_true", help="do not capture the QAT step in a CUDA graph")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how the shards' statistics are exchanged (fused peer-memory kernel, or NCCL all-gather)")

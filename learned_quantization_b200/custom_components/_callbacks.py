@@ -74,7 +74,7 @@ class NestedScaleTrackingCallback:
             f.write("".join(f"{v}\n" for v in values))
 
     def _codes(self, p, scale):
-        P, s = p.detach().contiguous(), scale.detach().contiguous()
+        P, s = ops.dense(p.detach()), scale.detach().contiguous()
         return ops.fq_fwd(P, s, codes_dtype=torch.float32)[1], ops.code_stats(P, s)
 
     def _dump_codes(self, p, scale, path_values, path_unique):

@@ -28,9 +28,9 @@ class _FakeQuant(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, parameter, scale, penalty_threshold, sgrad_mode):
-        P = parameter.detach().contiguous()
+        P = ops.dense(parameter.detach())            # stays as it lies in memory (e.g. an OHWI-stored kernel)
         s = scale.detach().contiguous()
-        layout = ops.group_layout(P.shape, s.shape)
+        layout = ops.tensor_layout(P, s.shape)
         y = ops.fq_fwd(P, s, layout)
         ctx.save_for_backward(P, s)
         ctx.layout, ctx.lam, ctx.mode, ctx.s_shape = layout, penalty_threshold, sgrad_mode, scale.shape
@@ -39,7 +39,7 @@ class _FakeQuant(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         P, s = ctx.saved_tensors
-        dy = dy.contiguous()
+        dy = ops.match_strides(dy, P)
         if ctx.mode == SGRAD_THRESHOLD:
             dX, ds = ops.fq_bwd_threshold(dy, P, s, ctx.lam, ctx.layout)
         else:
@@ -216,7 +216,16 @@ class Conv2DLayerBase(_HostLayer):
     _use_bias = True
 
     def _setup(self, seed, q_value, orientation, initializer, filters, kernel_size, strides, padding,
-               regularizer, trained_weights):
+               regularizer, trained_weights, kernel_storage: str = "hwio"):
+        """kernel_storage: "hwio" keeps the kernel in memory as the reference's TensorFlow
+        variable lies (kh, kw, Cin, Cout); "ohwi" keeps the SAME logical HWIO tensor -- same shape, same
+        values, same groups for every orientation -- in (Cout, kh, kw, Cin) memory order, which is what
+        cuDNN's channels-last convolutions read and write: the per-step transposes of every kernel and
+        of every kernel gradient disappear.  The quantisation kernels work on memory order either way
+        (ops.tensor_layout)."""
+        if kernel_storage not in ("hwio", "ohwi"):
+            raise ValueError("kernel_storage must be 'hwio' or 'ohwi'")
+        self.kernel_storage = kernel_storage
         self.seed = seed
         self.nested_q_k_layer = self._q_cls(**{self._q_arg: q_value}, initializer=None, orientation=orientation)
         if self._use_bias:
@@ -233,6 +242,9 @@ class Conv2DLayerBase(_HostLayer):
         tw = self.trained_weights if self.trained_weights else None      # NQ:314
         kernel_shape = (*self.kernel_size, input_shape[-1], self.filters)  # NQ:321
         self.kernel = self._init_weight(kernel_shape, tw[0] if tw else None, device)
+        if self.kernel_storage == "ohwi":
+            ohwi = self.kernel.detach().permute(3, 0, 1, 2).contiguous()
+            self.kernel = nn.Parameter(ohwi.permute(1, 2, 3, 0))          # logical HWIO, OHWI in memory
         self.nested_q_k_layer.build(tuple(self.kernel.shape), device)
         if self._use_bias:
             self.b = self._init_weight((self.filters,), tw[1] if tw else None, device)

@@ -53,4 +53,4 @@ class CustomConv2DLayer(_impl.Conv2DLayerBase):
         super().__init__()
         self.given_name = name
         self._setup(seed, penalty_rate, orientation, initializer, filters, kernel_size, strides, padding,
-                    regularizer, trained_weights)
+                    regularizer, trained_weights, kwargs.get("kernel_storage", "hwio"))

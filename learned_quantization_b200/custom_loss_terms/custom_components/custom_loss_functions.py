@@ -22,9 +22,9 @@ eps_float32 = ops.EPS_FLOAT32
 class _Penalty(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kind, *tensors):
-        Ps = [t.detach().contiguous() for t in tensors[0::2]]
+        Ps = [ops.dense(t.detach()) for t in tensors[0::2]]
         ss = [t.detach().contiguous() for t in tensors[1::2]]
-        layouts = [ops.group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+        layouts = [ops.tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
         out, ws = ops.penalty_fwd(kind, Ps, ss, layouts)
         ctx.kind, ctx.layouts, ctx.ws = kind, layouts, ws
         ctx.Ps, ctx.ss = Ps, ss

@@ -65,6 +65,33 @@ def group_layout(param_shape: Sequence[int], s_shape: Sequence[int]) -> Tuple[in
     return outer, param_shape[ax], inner
 
 
+def mem_perm(t: torch.Tensor) -> Optional[Tuple[int, ...]]:
+    """Dims of `t` ordered from the slowest to the fastest varying in MEMORY, if `t` is a permutation of
+    a contiguous tensor (e.g. a conv kernel of logical shape HWIO stored as OHWI, the order cuDNN's
+    channels-last kernels want); None otherwise.  Contiguous tensors give the identity."""
+    if t.is_contiguous():
+        return tuple(range(t.dim()))
+    perm = tuple(sorted(range(t.dim()), key=lambda d: (-t.stride(d), d)))
+    return perm if t.permute(perm).is_contiguous() else None
+
+
+def dense(t: torch.Tensor) -> torch.Tensor:
+    """`t` itself when its elements occupy one dense block of memory (in any dim order), else a contiguous copy."""
+    return t if mem_perm(t) is not None else t.contiguous()
+
+
+def same_layout(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Same shape and the same element at every memory offset (strides of size-1 dims do not matter)."""
+    return a.shape == b.shape and all(sa == sb or n == 1 for sa, sb, n in zip(a.stride(), b.stride(), a.shape))
+
+
+def match_strides(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """`t` laid out in memory exactly like `like` (same shape): a no-op when it already is."""
+    if same_layout(t, like):
+        return t
+    return torch.empty_like(like).copy_(t)
+
+
 def _require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if t is None:
@@ -74,8 +101,36 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
                                f"got a tensor on {t.device}")
         if t.dtype != torch.float32:
             raise TypeError(f"fp32 tensors only, got {t.dtype}")
-        if not t.is_contiguous():
-            raise ValueError("tensors must be contiguous")
+        if mem_perm(t) is None:
+            raise ValueError("tensors must be dense in memory (contiguous, or a permutation of a contiguous tensor)")
+
+
+def tensor_layout(P: torch.Tensor, s_shape: Sequence[int]) -> Tuple[int, int, int]:
+    """[outer, C, inner] of `P` AS IT LIES IN MEMORY for a scale of (logical) shape `s_shape`: the groups are
+    the same as group_layout's, only their position in the flat memory order changes when `P` is a permuted
+    view.  HWIO kernel stored as OHWI: channelwise -> [Co*kh*kw, Ci, 1], rowwise -> [Co, kh, kw*Ci],
+    columnwise -> [Co*kh, kw, Ci]."""
+    perm = mem_perm(P)
+    if perm is None:
+        raise ValueError("tensor is not dense in memory")
+    shape = tuple(int(d) for d in P.shape)
+    s_shape = tuple(int(d) for d in s_shape)
+    if perm == tuple(range(P.dim())):
+        return group_layout(shape, s_shape)
+    if len(s_shape) == 1 and len(shape) != 1 or all(d == 1 for d in s_shape):
+        group_layout(shape, s_shape)                   # validates
+        return 1, 1, P.numel()
+    ax = [i for i, d in enumerate(s_shape) if d != 1]
+    group_layout(shape, s_shape)                       # validates (one non-1 axis, sizes agree)
+    k = perm.index(ax[0])
+    mem_shape = [shape[d] for d in perm]
+    outer = 1
+    for d in mem_shape[:k]:
+        outer *= d
+    inner = 1
+    for d in mem_shape[k + 1:]:
+        inner *= d
+    return outer, mem_shape[k], inner
 
 
 def _stream() -> int:
@@ -119,12 +174,14 @@ def fq_fwd(P: torch.Tensor, s: torch.Tensor, layout=None, *, codes_dtype: Option
            out: Optional[torch.Tensor] = None):
     """y = floor(P / s) * s (NQ:55-60).  Returns y, or (y, codes) when codes_dtype is given."""
     _require_cuda(P, s)
-    layout = layout or group_layout(P.shape, s.shape)
-    y = torch.empty_like(P) if out is None else out
+    layout = layout or tensor_layout(P, s.shape)
+    y = torch.empty_like(P) if out is None else out          # same strides as P: element i of memory <-> element i
+    if not same_layout(y, P):
+        raise ValueError("out must be laid out in memory like P")
     codes, cd = None, _lib.LQ_CODES_NONE
     if codes_dtype is not None:
         cd = {torch.float32: _lib.LQ_CODES_F32, torch.int32: _lib.LQ_CODES_I32, torch.int8: _lib.LQ_CODES_I8}[codes_dtype]
-        codes = torch.empty(P.shape, dtype=codes_dtype, device=P.device)
+        codes = torch.empty_like(P, dtype=codes_dtype)
     with torch.cuda.device(P.device):
         check(lib.lq_fq_fwd(P.data_ptr(), s.data_ptr(), y.data_ptr(),
                             None if codes is None else codes.data_ptr(), cd,
@@ -137,7 +194,8 @@ def fq_bwd_threshold(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, penalty
                      round_mode: int = _lib.LQ_ROUND_FLOOR, qmin: float = NEG_INF, qmax: float = POS_INF):
     """(dX, ds) of NQ:62-118.  dX is dy itself unless write_dx asks for a separate copy."""
     _require_cuda(dy, P, s)
-    layout = layout or group_layout(P.shape, s.shape)
+    layout = layout or tensor_layout(P, s.shape)
+    dy = match_strides(dy, P)
     ds = torch.empty_like(s)
     dX = torch.empty_like(dy) if write_dx else None
     d = make_desc(layout=layout)
@@ -156,7 +214,8 @@ def fq_bwd_threshold_stats(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, p
     """One SHARD of a tensor split along `outer`: (dX, stats) with stats[g] = {sum, n_below, max|q|}
     (float64 [C, 3]).  Gather the shards' stats and call fq_bwd_threshold_finish."""
     _require_cuda(dy, P, s)
-    layout = layout or group_layout(P.shape, s.shape)
+    layout = layout or tensor_layout(P, s.shape)
+    dy = match_strides(dy, P)
     if stats is None:
         stats = torch.empty((layout[1], 3), dtype=torch.float64, device=P.device)
     dX = torch.empty_like(dy) if write_dx else None
@@ -204,7 +263,9 @@ def scale_constraint_(s: torch.Tensor, min_value: float = SCALE_INIT) -> torch.T
 def mt_fq_fwd(Ps: Sequence[torch.Tensor], ss: Sequence[torch.Tensor], ys: Sequence[torch.Tensor],
               layouts=None, round_mode=_lib.LQ_ROUND_FLOOR, qmin=NEG_INF, qmax=POS_INF) -> None:
     _require_cuda(*Ps, *ss, *ys)
-    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    layouts = layouts or [tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
+    if any(not same_layout(y, p) for y, p in zip(ys, Ps)):
+        raise ValueError("every y must be laid out in memory like its P")
     arr = desc_array([make_desc(P=p, s=s, y=y, layout=l) for p, s, y, l in zip(Ps, ss, ys, layouts)])
     with torch.cuda.device(Ps[0].device):
         check(lib.lq_mt_fq_fwd(arr, len(arr), round_mode, qmin, qmax, _stream()))
@@ -214,7 +275,9 @@ def mt_fq_bwd(dys, Ps, ss, dss, penalty_threshold: float, layouts=None, dXs=None
               scale_grad_mode=_lib.LQ_SGRAD_THRESHOLD, round_mode=_lib.LQ_ROUND_FLOOR,
               qmin=NEG_INF, qmax=POS_INF) -> None:
     _require_cuda(*dys, *Ps, *ss, *dss)
-    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    layouts = layouts or [tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
+    if any(not same_layout(dy, p) for dy, p in zip(dys, Ps)):
+        raise ValueError("every dy must be laid out in memory like its P (ops.match_strides)")
     dXs = dXs or [None] * len(Ps)
     arr = desc_array([make_desc(P=p, s=s, dy=dy, dX=dx, ds=ds, layout=l)
                       for p, s, dy, dx, ds, l in zip(Ps, ss, dys, dXs, dss, layouts)])
@@ -229,7 +292,7 @@ def mt_fq_bwd(dys, Ps, ss, dss, penalty_threshold: float, layouts=None, dXs=None
 def penalty_fwd(kind: int, Ps, ss, layouts=None):
     """compute_*_penalty() over tensors (LF:75-116 / 161-195 / 240-275). Returns (scalar, ws)."""
     _require_cuda(*Ps, *ss)
-    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    layouts = layouts or [tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
     arr = desc_array([make_desc(P=p, s=s, layout=l) for p, s, l in zip(Ps, ss, layouts)])
     need = workspace_bytes(arr, _lib.LQ_PHASE_PENALTY_FWD)
     ws = torch.empty(max(need, 256), dtype=torch.uint8, device=Ps[0].device)   # kept for the backward
@@ -244,7 +307,7 @@ def penalty_bwd(kind: int, Ps, ss, ws: torch.Tensor, upstream: float = 1.0,
                 accumulate: bool = False):
     """Gradients of upstream*penalty w.r.t. every P and s. Returns (dXs, dss)."""
     _require_cuda(*Ps, *ss)
-    layouts = layouts or [group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+    layouts = layouts or [tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
     need_dx = kind != _lib.LQ_PEN_INVERSE
     if dXs is None:
         dXs = [torch.empty_like(p) if need_dx else None for p in Ps]
@@ -337,7 +400,7 @@ def code_stats(P: torch.Tensor, s: torch.Tensor, layout=None, *, max_bins: int =
     int8 (utils/log_scripts.py:74-79 casts with .astype(np.int8), which wraps silently).
     Two passes over P (range, then histogram); only the non-empty bins come back to the host."""
     _require_cuda(P, s)
-    layout = layout or group_layout(P.shape, s.shape)
+    layout = layout or tensor_layout(P, s.shape)
     dev = P.device
     mm = torch.empty(2, dtype=torch.float32, device=dev)
     ws = workspace(256, dev, "codes")

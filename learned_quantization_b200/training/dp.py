@@ -140,15 +140,22 @@ class TorchDistComm(Comm):
 class GradBucket:
     """One flat fp32 buffer with views for every gradient, in the order [dy | plain | ds]."""
 
-    def __init__(self, quant_shapes: Sequence[Sequence[int]], plain_shapes: Sequence[Sequence[int]],
-                 scale_shapes: Sequence[Sequence[int]], device, align: int = 4):
-        def carve(shapes, off):
+    def __init__(self, quant_shapes: Sequence, plain_shapes: Sequence, scale_shapes: Sequence, device, align: int = 4):
+        """Each entry is a shape, or a tensor whose memory layout the view must reproduce (a kernel stored
+        as OHWI keeps that order inside the bucket: copies into it and the optimizer stay flat)."""
+        def carve(items, off):
             spans = []
-            for shp in shapes:
+            for it in items:
+                shp = tuple(int(d) for d in (it.shape if isinstance(it, torch.Tensor) else it))
+                perm = None
+                if isinstance(it, torch.Tensor) and not it.is_contiguous():
+                    perm = tuple(sorted(range(it.dim()), key=lambda d: (-it.stride(d), d)))
+                    if not it.permute(perm).is_contiguous():
+                        raise ValueError("bucket views can only mirror dense tensors")
                 n = 1
                 for d in shp:
-                    n *= int(d)
-                spans.append((off, n, tuple(int(d) for d in shp)))
+                    n *= d
+                spans.append((off, n, shp, perm))
                 off += -(-n // align) * align        # keep every view 16-byte aligned for the 128-bit paths
             return spans, off
         q, off = carve(quant_shapes, 0)
@@ -157,7 +164,13 @@ class GradBucket:
         s, off = carve(scale_shapes, off)
         self.n_total = off
         self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
-        view = lambda span: self.flat[span[0]:span[0] + span[1]].view(span[2])
+        def view(span):
+            off, n, shp, perm = span
+            base = self.flat[off:off + n]
+            if perm is None:
+                return base.view(shp)
+            inv = [perm.index(d) for d in range(len(shp))]
+            return base.view([shp[d] for d in perm]).permute(inv)
         self.dy = [view(x) for x in q]
         self.plain = [view(x) for x in p]
         self.ds = [view(x) for x in s]

@@ -86,13 +86,13 @@ class MnistMLP(nn.Module):
 class _ResidualBlock(nn.Module):
     """experiment.py:627-704: conv-bn-relu, conv-bn, (1x1 conv-bn shortcut when strided), add, relu."""
 
-    def __init__(self, L, kw, cin, filters, orientation, stride, seed):
+    def __init__(self, L, kw, cin, filters, orientation, stride, seed, storage):
         super().__init__()
         init = RandomNormal(seed=seed)
         reg = regularizers.l2(1e-4)
         mk = lambda ks, st, nm: L.CustomConv2DLayer(seed=seed, orientation=orientation, initializer=init, filters=filters,
                                                     kernel_size=ks, strides=st, padding="same", name=nm,
-                                                    regularizer=reg, **kw)
+                                                    regularizer=reg, kernel_storage=storage, **kw)
         self.c1, self.b1 = mk((3, 3), stride, "conv_0"), _BN(filters)
         self.c2, self.b2 = mk((3, 3), (1, 1), "conv_1"), _BN(filters)
         self.short = None
@@ -113,18 +113,19 @@ class ImagenetteResNet(nn.Module):
     (64,64,128,128,256,256,512,512), dropout .3, GAP, dropout .3, Dense(10, softmax).
     20 quantised convs with bias -> 40 quantised tensors per step."""
 
-    def __init__(self, value: float, seed: int, orientation: str, variant: str = "nested", num_classes: int = 10):
+    def __init__(self, value: float, seed: int, orientation: str, variant: str = "nested", num_classes: int = 10,
+                 kernel_storage: str = "hwio"):
         super().__init__()
         L = _layers(variant)
         kw = _q_kwargs(variant, value)
         init = RandomNormal(seed=seed)
         self.stem = L.CustomConv2DLayer(seed=seed, orientation=orientation, initializer=init, filters=64,
                                         kernel_size=(7, 7), strides=(2, 2), padding="same",
-                                        name="custom_conv2d_layer_64_0", regularizer=None, **kw)
+                                        name="custom_conv2d_layer_64_0", regularizer=None, kernel_storage=kernel_storage, **kw)
         self.bn = _BN(64)
         cfg = [(64, 64, (1, 1)), (64, 64, (1, 1)), (64, 128, (2, 2)), (128, 128, (1, 1)),
                (128, 256, (2, 2)), (256, 256, (1, 1)), (256, 512, (2, 2)), (512, 512, (1, 1))]
-        self.blocks = nn.ModuleList(_ResidualBlock(L, kw, ci, co, orientation, st, seed) for ci, co, st in cfg)
+        self.blocks = nn.ModuleList(_ResidualBlock(L, kw, ci, co, orientation, st, seed, kernel_storage) for ci, co, st in cfg)
         self.fc = nn.Linear(512, num_classes)
         with torch.no_grad():
             self.fc.weight.copy_(init((num_classes, 512)))
@@ -208,8 +209,8 @@ def mnist_mlp(value, seed=42, orientation="rowwise", variant="nested"):
     return MnistMLP(value, seed, orientation, variant)
 
 
-def imagenette_resnet(value, seed=42, orientation="channelwise", variant="nested"):
-    return ImagenetteResNet(value, seed, orientation, variant)
+def imagenette_resnet(value, seed=42, orientation="channelwise", variant="nested", kernel_storage="hwio"):
+    return ImagenetteResNet(value, seed, orientation, variant, kernel_storage=kernel_storage)
 
 
 def cifar_resnet18(penalty_threshold=0.0, seed=42, orientation="scalar"):

@@ -50,7 +50,7 @@ class QuantBank:
         self.params = [p for _, _, p, _ in self.pairs]
         self.qlayers = [q for _, _, _, q in self.pairs]
         self.scales = [q.scale for q in self.qlayers]
-        self.layouts = [ops.group_layout(p.shape, s.shape) for p, s in zip(self.params, self.scales)]
+        self.layouts = [ops.tensor_layout(p, s.shape) for p, s in zip(self.params, self.scales)]
         modes = {q._sgrad_mode for q in self.qlayers}
         lams = {float(q._threshold() or 0.0) for q in self.qlayers}
         if len(modes) != 1 or len(lams) != 1:
@@ -60,8 +60,13 @@ class QuantBank:
         total = sum(-(-p.numel() // 4) * 4 for p in self.params)
         self._yflat = torch.empty(total, dtype=torch.float32, device=dev)
         self.ys, off = [], 0
-        for p in self.params:
-            self.ys.append(self._yflat[off:off + p.numel()].view(p.shape).requires_grad_(True))
+        for p in self.params:                       # y_i mirrors P_i's memory layout inside the flat buffer
+            perm = ops.mem_perm(p)
+            if perm is None:
+                raise ValueError("quantised parameters must be dense in memory")
+            inv = [perm.index(d) for d in range(p.dim())]
+            y = self._yflat[off:off + p.numel()].view([p.shape[d] for d in perm]).permute(inv)
+            self.ys.append(y.requires_grad_(True))
             off += -(-p.numel() // 4) * 4
 
     def forward(self) -> None:
@@ -102,8 +107,7 @@ class TrainStep:
         quant_ids = {id(p) for p in b.params} | {id(s) for s in b.scales}
         self.plain = [p for p in model.parameters() if id(p) not in quant_ids and p.requires_grad]
         dev = b.params[0].device
-        self.bucket = GradBucket([p.shape for p in b.params], [p.shape for p in self.plain],
-                                 [s.shape for s in b.scales], dev)
+        self.bucket = GradBucket(list(b.params), [p.shape for p in self.plain], [s.shape for s in b.scales], dev)
         # optimizer table over [P | plain | s], gradients = the bucket views (pointers never change)
         l2 = []
         for host in b.hosts:

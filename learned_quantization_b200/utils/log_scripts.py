@@ -29,7 +29,7 @@ def quantized_parameters(model):
         else:
             continue
         for tag, p, q in pairs:
-            P, s = p.detach().contiguous(), q.scale.detach().contiguous()
+            P, s = ops.dense(p.detach()), q.scale.detach().contiguous()
             weights[f"{m.name}/{tag}"] = ops.codes_int8(P, s).cpu().numpy()
             st = ops.code_stats(P, s)
             if st["int8_overflow"]:

@@ -382,3 +382,67 @@ def test_tracking_callbacks_write_the_reference_log_files(lq, tmp_path):
     a = cb.AccuracyLossTrackingCallBack(str(tmp_path))
     a.on_epoch_end(0, {"val_accuracy": 0.5, "val_loss": 1.0, "accuracy": 0.25, "loss": 2.0})
     assert open(tmp_path / "accuracy" / "train_accuracy.log").read() == "Epoch 0\n0.25\n"
+
+
+# ------------------------------------------------------------------ f3: kernels stored in cuDNN's order
+@pytest.mark.parametrize("orientation", ["channelwise", "rowwise", "columnwise", "scalar"])
+def test_ohwi_kernel_storage_is_the_same_operator(lq, orientation):
+    """A kernel kept in (Cout, kh, kw, Cin) memory order is the same logical HWIO tensor with the same groups:
+    fake-quant output, dP and ds equal the HWIO-stored layer's, per layer and through the bank."""
+    from learned_quantization_b200 import RandomNormal
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training.step import TrainStep
+
+    class Net(torch.nn.Module):
+        def __init__(self, storage):
+            super().__init__()
+            init = RandomNormal(seed=5)
+            self.c1 = nq.CustomConv2DLayer(seed=5, penalty_threshold=1e-3, orientation=orientation, initializer=init,
+                                           filters=16, kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
+                                           regularizer=None, kernel_storage=storage)
+            self.c2 = nq.CustomConv2DLayer(seed=5, penalty_threshold=1e-3, orientation=orientation, initializer=init,
+                                           filters=10, kernel_size=(3, 3), strides=(2, 2), padding="same", name="b",
+                                           regularizer=None, kernel_storage=storage)
+            self.c3 = nq.CustomConv2DLayer(seed=5, penalty_threshold=1e-3, orientation=orientation, initializer=init,
+                                           filters=10, kernel_size=(1, 1), strides=(1, 1), padding="same", name="c",
+                                           regularizer=None, kernel_storage=storage)     # size-1 dims: ambiguous strides
+
+        def forward(self, x):
+            return torch.softmax(self.c3(self.c2(torch.relu(self.c1(x)))).mean(dim=(1, 2)), dim=-1)
+
+    x = torch.rand(4, 12, 12, 8, device="cuda")
+    y = torch.randint(0, 10, (4,), device="cuda")
+    nets = {}
+    for storage in ("hwio", "ohwi"):
+        net = Net(storage).cuda()
+        net(x)
+        nets[storage] = net
+    a, b = nets["hwio"], nets["ohwi"]
+    assert b.c1.kernel.shape == a.c1.kernel.shape and not b.c1.kernel.is_contiguous()
+    assert b.c1.kernel.permute(3, 0, 1, 2).is_contiguous()
+    with torch.no_grad():
+        for la, lb in ((a.c1, b.c1), (a.c2, b.c2), (a.c3, b.c3)):
+            lb.kernel.copy_(la.kernel); lb.b.copy_(la.b)
+            for qa, qb in ((la.nested_q_k_layer, lb.nested_q_k_layer), (la.nested_q_b_layer, lb.nested_q_b_layer)):
+                qa.scale.uniform_(5e-3, 2e-2); qb.scale.copy_(qa.scale)
+    # the operator itself: bit-identical values at the same logical positions
+    ya = a.c1.nested_q_k_layer(a.c1.kernel)
+    yb = b.c1.nested_q_k_layer(b.c1.kernel)
+    assert lq.ops.same_layout(yb, b.c1.kernel) and torch.equal(ya, yb)
+    grads = {}
+    for name, net in nets.items():
+        for p in net.parameters():
+            p.grad = None
+        scce(y, net(x)).mean().backward()
+        grads[name] = [p.grad.clone() for p in net.parameters()]
+    for ga, gb in zip(grads["hwio"], grads["ohwi"]):
+        assert float((ga - gb).abs().max()) <= 1e-4 * max(float(ga.abs().max()), 1e-30) + 1e-12
+    # through the bank: gradients land in the bucket in OHWI order, parameters update identically
+    steps = {k: TrainStep(n, scce, optimizer="adam", lr=1e-3) for k, n in nets.items()}
+    for k in steps:
+        steps[k](x, y)
+    assert lq.ops.same_layout(steps["ohwi"].bucket.dy[0], b.c1.kernel)
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert float((pa - pb).abs().max()) <= 1e-5 * max(float(pa.abs().max()), 1e-30) + 1e-9
