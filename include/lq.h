@@ -180,6 +180,12 @@ int lq_code_histogram(const float* P, const float* s, int64_t outer, int64_t C, 
                       int round_mode, float qmin, float qmax, int64_t code_lo, int64_t nbins,
                       uint32_t* hist, unsigned long long* outside, lq_stream_t stream);
 
+/* SURVEY 8(f3), bias path: out[c] = sum_r x[r*cols + c] for a row-major fp32 matrix -- the gradient of
+ * the quantised bias in conv2d(x, qk) + qb (NQ:343-350) is the column sum of the NHWC output gradient
+ * seen as [N*H*W, Cout].  Deterministic two-stage reduction; ws >= lq_colsum_workspace_bytes. */
+int lq_colsum_workspace_bytes(int64_t rows, int64_t cols, size_t* out_bytes);
+int lq_colsum(const float* x, int64_t rows, int64_t cols, float* out, void* ws, size_t ws_bytes, lq_stream_t stream);
+
 /* Host-buffer entry point (the end-to-end path bench.py times): pinned or pageable HOST
  * arrays in, HOST arrays out; chunks are staged through the caller's device workspace
  * (>= lq_host_workspace_bytes) on internal streams, copies overlapped with the kernels.

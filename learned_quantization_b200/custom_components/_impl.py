@@ -124,6 +124,39 @@ def _same_pad(n: int, k: int, s: int) -> Tuple[int, int]:
     return total // 2, total - total // 2
 
 
+class _ConvBias(torch.autograd.Function):
+    """conv2d + bias on cuDNN with the bias gradient from lq_colsum: the output gradient of an NHWC
+    convolution is a [N*H*W, Cout] matrix in memory and d(bias) its column sums; the framework's generic
+    reduction took ~43 us per layer for it (13 % of the IMAGENETTE step)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.conv = (tuple(stride), tuple(padding))
+        return F.conv2d(x, w, bias, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding = ctx.conv
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gy, x, w, None, stride, padding, (1, 1), False, (0, 0), 1,
+            (ctx.needs_input_grad[0], ctx.needs_input_grad[1], False))
+        gb = None
+        if ctx.needs_input_grad[2]:
+            g = gy.permute(0, 2, 3, 1)                   # NHWC: contiguous when gy is channels-last
+            if not g.is_contiguous():
+                g = g.contiguous()
+            gb = ops.colsum(g.reshape(-1, g.shape[-1]))
+        return gx, gw, gb, None, None
+
+
+def _conv(x, w, bias, stride, padding):
+    if bias is None or not x.is_cuda:
+        return F.conv2d(x, w, bias, stride=stride, padding=padding)
+    return _ConvBias.apply(x, w, bias, stride, padding)
+
+
 def conv2d_nhwc(inputs, kernel_hwio, strides, padding: str, bias=None):
     """tf.nn.conv2d semantics (NHWC activations, HWIO filters, TF 'SAME' padding) on cuDNN.
     `bias` is added in the convolution's epilogue: the same single fp32 add per
@@ -138,11 +171,11 @@ def conv2d_nhwc(inputs, kernel_hwio, strides, padding: str, bias=None):
         pt, pb = _same_pad(x.shape[2], w.shape[2], sh)
         pl, pr = _same_pad(x.shape[3], w.shape[3], sw)
         if pt == pb and pl == pr:
-            y = F.conv2d(x, w, bias, stride=(sh, sw), padding=(pt, pl))
+            y = _conv(x, w, bias, (sh, sw), (pt, pl))
         else:
-            y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, bias, stride=(sh, sw))
+            y = _conv(F.pad(x, (pl, pr, pt, pb)), w, bias, (sh, sw), (0, 0))
     elif padding.upper() == "VALID":
-        y = F.conv2d(x, w, bias, stride=(sh, sw))
+        y = _conv(x, w, bias, (sh, sw), (0, 0))
     else:
         raise ValueError(f"padding must be 'same' or 'valid', got {padding!r}")
     return y.permute(0, 2, 3, 1)

@@ -435,3 +435,18 @@ def codes_int8(P: torch.Tensor, s: torch.Tensor, layout=None) -> torch.Tensor:
     """floor(P / s).astype(int8) with numpy's wrap-around (utils/log_scripts.py:74-79), on the device."""
     _, codes = fq_fwd(P, s, layout, codes_dtype=torch.int8)
     return codes
+
+
+# --------------------------------------------------------------------- bias gradient (SURVEY 8 f3)
+def colsum(x2d: torch.Tensor) -> torch.Tensor:
+    """Column sums of a contiguous fp32 [rows, cols] CUDA matrix (the bias gradient of an NHWC convolution)."""
+    if not x2d.is_cuda or x2d.dtype != torch.float32 or x2d.dim() != 2 or not x2d.is_contiguous():
+        raise ValueError("colsum takes a contiguous fp32 CUDA matrix")
+    rows, cols = x2d.shape
+    need = C.c_size_t()
+    check(lib.lq_colsum_workspace_bytes(rows, cols, C.byref(need)))
+    ws = workspace(need.value, x2d.device, "colsum")
+    out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        check(lib.lq_colsum(x2d.data_ptr(), rows, cols, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out

@@ -446,3 +446,30 @@ def test_ohwi_kernel_storage_is_the_same_operator(lq, orientation):
     assert lq.ops.same_layout(steps["ohwi"].bucket.dy[0], b.c1.kernel)
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert float((pa - pb).abs().max()) <= 1e-5 * max(float(pa.abs().max()), 1e-30) + 1e-9
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (257, 3), (64 * 56 * 56, 64), (4097, 512), (1000, 10), (12345, 130)])
+def test_colsum_is_the_bias_gradient(lq, rows, cols):
+    x = torch.randn(rows, cols, device="cuda")
+    got = lq.ops.colsum(x)
+    want = x.double().sum(dim=0)
+    assert float((got.double() - want).abs().max()) <= 1e-6 * max(float(want.abs().max()), 1.0) * max(1.0, rows ** 0.5 / 30)
+    assert torch.equal(got, lq.ops.colsum(x)), "deterministic"
+
+
+def test_conv_bias_gradient_matches_autograd(lq):
+    from learned_quantization_b200.custom_components._impl import conv2d_nhwc
+    torch.manual_seed(3)
+    x = torch.randn(4, 14, 14, 8, device="cuda", requires_grad=True)
+    k = torch.randn(3, 3, 8, 16, device="cuda", requires_grad=True)
+    b = torch.randn(16, device="cuda", requires_grad=True)
+    for strides, pad in (((1, 1), "same"), ((2, 2), "same"), ((1, 1), "valid")):
+        for t in (x, k, b):
+            t.grad = None
+        conv2d_nhwc(x, k, strides, pad, bias=b).square().sum().backward()
+        got = [t.grad.clone() for t in (x, k, b)]
+        for t in (x, k, b):
+            t.grad = None
+        (conv2d_nhwc(x, k, strides, pad) + b).square().sum().backward()
+        for g, t in zip(got, (x, k, b)):
+            assert float((g - t.grad).abs().max()) <= 1e-4 * float(t.grad.abs().max())

@@ -23,7 +23,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
-    net = models.imagenette_resnet(1e-11, orientation="channelwise").cuda().train()
+    net = models.imagenette_resnet(1e-11, orientation="channelwise", kernel_storage="ohwi").cuda().train()
     x, y = models.synthetic_batch(args.batch, (224, 224, 3), "cuda")
     with torch.no_grad():
         net(x[:2])
