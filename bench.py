@@ -364,7 +364,7 @@ def run_ours(args):
                              "roofline: a second pass, K forward launches between two events, then K backward launches "
                              "(element kernel + second stage) between two events",
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_kernel, 512 blocks)",
+            "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_warp_kernel, its second stage)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": BYTES_BWD * n},
