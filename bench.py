@@ -159,6 +159,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its children; this arm is one process and uses every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sample_outer = 32     # 8 Mi elements per step
     layout, P, s, dy = cpu_sample(sample_outer)
     for _ in range(args.warmup):
