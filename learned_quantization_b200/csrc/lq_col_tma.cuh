@@ -244,12 +244,9 @@ int col_tma_launch(const Geom& g, const float* dy, const float* P, const float* 
   if ((rc = make_map_2d(&mP, P, g.outer, g.W, tile_rows, g.bx))) return rc;
   if ((rc = make_map_2d(&mD, dy, g.outer, g.W, tile_rows, g.bx))) return rc;
   if ((rc = make_map_2d(&mX, j.write_dx ? dX : dy, g.outer, g.W, tile_rows, g.bx))) return rc;
-  static bool configured = false;   // per Op instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(col_tma_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColTmaSmem));
-    if (e != cudaSuccess) return cuda_fail(e, "col_tma smem attribute");
-    configured = true;
-  }
+  // per device and per function; a host-side table update, so simply done on every launch
+  cudaError_t e = cudaFuncSetAttribute(col_tma_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ColTmaSmem));
+  if (e != cudaSuccess) return cuda_fail(e, "col_tma smem attribute");
   col_tma_kernel<Op><<<dim3((unsigned)g.nblocks), dim3(kThreads), sizeof(ColTmaSmem), st>>>(j, op, mP, mD, mX);
   return cuda_fail(cudaGetLastError(), "col_tma launch");
 }
