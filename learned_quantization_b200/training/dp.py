@@ -97,11 +97,30 @@ class P2PFinish:
         self.rank, self.world = int(rank), int(world)
         self._h = C.c_void_p()
         mine = C.create_string_buffer(64)
-        check(lib.lq_p2p_create(self.rank, self.world, int(max_groups), C.byref(self._h), mine))
+        # every rank reaches every collective below whatever happens locally: a failure on one rank
+        # (IPC not permitted in this container, out of memory, ...) raises on ALL ranks instead of hanging
+        err = None
+        try:
+            check(lib.lq_p2p_create(self.rank, self.world, int(max_groups), C.byref(self._h), mine))
+        except _lib.LqError as e:
+            err = str(e)
         if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(mine.raw))
-            check(lib.lq_p2p_connect(self._h, b"".join(handles)))
+            got = [None] * self.world
+            dist.all_gather_object(got, (err, bytes(mine.raw)))
+            errs = [e for e, _ in got if e]
+            if not errs:
+                try:
+                    check(lib.lq_p2p_connect(self._h, b"".join(h for _, h in got)))
+                except _lib.LqError as e:
+                    err = str(e)
+                got2 = [None] * self.world
+                dist.all_gather_object(got2, err)
+                errs = [e for e in got2 if e]
+            if errs:
+                self.close()
+                raise _lib.LqError(_lib.LQ_OK - 5, "peer-memory exchange unavailable: " + errs[0])
+        elif err:
+            raise _lib.LqError(_lib.LQ_OK - 5, err)
 
     def finish(self, local_stats: torch.Tensor, penalty_threshold: float, n_per_group: float, ds: torch.Tensor) -> torch.Tensor:
         if local_stats.dtype != torch.float64 or not local_stats.is_cuda or not local_stats.is_contiguous():
