@@ -1,0 +1,85 @@
+"""CPU tier: host-side layout logic (no kernels run): the [outer, C, inner] view of a tensor as it lies in
+memory, for contiguous tensors and for kernels stored in cuDNN's order, against a brute-force group map."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lq_oracle as o
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import learned_quantization_b200 as pkg
+    return pkg.ops
+
+
+def brute_force_groups(t, s_shape):
+    """group id of every element in MEMORY order, from the logical broadcasting rule of NQ:56-58."""
+    gid = torch.arange(int(np.prod(s_shape))).reshape(s_shape)
+    logical = gid.expand(t.shape) if len(s_shape) == t.dim() else gid.reshape([1] * t.dim()).expand(t.shape)
+    perm = sorted(range(t.dim()), key=lambda d: (-t.stride(d), d))
+    return logical.permute(perm).reshape(-1).numpy()
+
+
+@pytest.mark.parametrize("orientation", ["rowwise", "columnwise", "channelwise", "scalar"])
+@pytest.mark.parametrize("storage", ["hwio", "ohwi", "dense2d", "bias"])
+def test_tensor_layout_matches_the_broadcasting_rule(ops, orientation, storage):
+    if storage == "hwio":
+        t = torch.zeros(3, 2, 5, 4)
+    elif storage == "ohwi":
+        t = torch.zeros(4, 3, 2, 5).permute(1, 2, 3, 0)
+        assert t.shape == (3, 2, 5, 4) and not t.is_contiguous()
+    elif storage == "dense2d":
+        t = torch.zeros(6, 7)
+    else:
+        t = torch.zeros(9)
+    if t.dim() < 3 and orientation == "channelwise" and t.dim() < 2:
+        pytest.skip("a bias only ever takes the scalar scale")
+    try:
+        s_shape = o.scale_shape(tuple(t.shape), orientation)
+    except Exception:
+        pytest.skip("orientation not defined for this rank")
+    if len(s_shape) != 1 and len(s_shape) != t.dim():
+        pytest.skip("not broadcastable")
+    outer, C, inner = ops.tensor_layout(t, s_shape)
+    assert outer * C * inner == t.numel()
+    idx = np.arange(t.numel())
+    got = (idx // inner) % C
+    want = brute_force_groups(t, s_shape)
+    # same partition of the elements into groups, with the same numbering
+    assert np.array_equal(got, want), (storage, orientation, (outer, C, inner))
+    if t.is_contiguous():
+        assert (outer, C, inner) == o.group_layout(tuple(t.shape), tuple(s_shape))
+
+
+def test_mem_perm_dense_and_match_strides(ops):
+    a = torch.arange(24.0).reshape(2, 3, 4)
+    assert ops.mem_perm(a) == (0, 1, 2)
+    b = a.permute(2, 0, 1)
+    assert ops.mem_perm(b) == (1, 2, 0) and ops.dense(b) is b
+    c = a[:, ::2]                               # not a permutation of a contiguous block
+    assert ops.mem_perm(c) is None and ops.dense(c).is_contiguous()
+    d = ops.match_strides(a.permute(2, 0, 1).contiguous(), b)
+    assert d.stride() == b.stride() and torch.equal(d, b)
+    one = torch.zeros(5, 1, 1, 7).permute(1, 2, 3, 0)     # size-1 dims have arbitrary strides
+    like = torch.zeros(1, 1, 7, 5)
+    assert ops.same_layout(one.contiguous(), like)
+    with pytest.raises(ValueError):
+        ops.group_layout((3, 4), (3, 4))        # two non-1 axes
+    with pytest.raises(ValueError):
+        ops.scale_shape((3, 3), "diagonal")
+
+
+def test_grad_bucket_mirrors_parameter_memory():
+    from learned_quantization_b200.training.dp import GradBucket
+    k = torch.arange(4 * 3 * 2 * 5, dtype=torch.float32).reshape(4, 3, 2, 5).permute(1, 2, 3, 0)    # logical HWIO
+    b = GradBucket([k, (6,)], [(2, 2)], [(1, 1, 5, 1), (1,)], "cpu")
+    assert b.dy[0].shape == k.shape and b.dy[0].stride() == k.stride()
+    b.dy[0].copy_(k)
+    flat = b.flat[: k.numel()]
+    assert torch.equal(flat, torch.arange(float(k.numel())))   # memory order of the bucket == memory order of k
+    offs = [v.data_ptr() - b.flat.data_ptr() for v in b.dy + b.plain + b.ds]
+    assert offs == sorted(offs) and all(o_ % 16 == 0 for o_ in offs)
+    assert b.exact_part().numel() == offs[3] // 4 and b.all().numel() >= b.exact_part().numel() + 5 + 1
