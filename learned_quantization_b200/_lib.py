@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblq.so")
+# LQ_LIBRARY points at an alternative build of the same ABI (kernel A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("LQ_LIBRARY") or os.path.join(_HERE, "csrc", "liblq.so")
 
 LQ_OK = 0
 LQ_ROUND_FLOOR, LQ_ROUND_RNE = 0, 1
