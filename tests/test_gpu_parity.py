@@ -231,6 +231,43 @@ def test_random_vs_oracle(lq, shape, s_shape, lam):
     assert bits_equal(host(ds), host(ds_b)), "second-stage reduction must be deterministic"
 
 
+def _fuzz_shapes():
+    rng = np.random.default_rng(20261018)
+    shapes = []
+    for _ in range(36):                                   # small: every traversal, tails, odd sizes
+        outer = int(rng.integers(1, 700))
+        C = int(rng.choice([1, 2, 3, 5, 8, 16, 33, 64, 130]))
+        inner = int(rng.choice([1, 2, 3, 4, 7, 16, 63, 64, 127, 128, 129, 512, 1000, 4097]))
+        if outer * C * inner <= 300_000:
+            shapes.append((outer, C, inner))
+    for _ in range(8):                                    # TMA-staged COL backward: >= 1 Mi elements, W % 4 == 0
+        W = int(rng.choice([32, 36, 64, 100, 128, 132, 260, 1028]))
+        inner = int(rng.choice([d for d in (1, 2, 4) if W % d == 0]))
+        outer = int(rng.integers((1 << 20) // W + 1, (3 << 19) // W + 600))
+        shapes.append((outer, W // inner, inner))
+    return shapes
+
+
+@pytest.mark.parametrize("layout", _fuzz_shapes())
+def test_fuzzed_layouts_vs_oracle(lq, layout):
+    ops = lq.ops
+    outer, C, inner = layout
+    rng = np.random.default_rng(outer * 1_000_003 + C * 1009 + inner)
+    P = rng.normal(0, 0.05, size=layout).astype(np.float32)
+    P.reshape(-1)[:: 11] = 0.0
+    dy = rng.normal(0, 1e-3, size=layout).astype(np.float32)
+    s = rng.uniform(5e-3, 2e-2, size=(1, C, 1)).astype(np.float32)
+    lam = float(rng.choice([1e-3, 1e-10, 0.05]))
+    q_ref, y_ref = o.fq_forward(P, s)
+    _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, lam, accum="fp64")
+    Pd, sd, dyd = dev(P), dev(s), dev(dy)
+    y = ops.fq_fwd(Pd, sd, layout)
+    assert bits_equal(host(y), y_ref)
+    dX, ds = ops.fq_bwd_threshold(dyd, Pd, sd, lam, layout, write_dx=True)
+    assert bits_equal(host(dX), dy)
+    assert ds_close(host(ds).reshape(-1), ds_ref.reshape(-1)), (layout, lam)
+
+
 def divcheck(lq, s_bits, a_sign_exp_bits):
     """(mismatches, pairs checked, first bad pair) of the kernels' hoisted-reciprocal division
     vs __fdiv_rn over all 2^23 dividend mantissas for every divisor in s_bits."""
