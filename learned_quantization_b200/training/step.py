@@ -212,6 +212,10 @@ class TrainStep:
             raise RuntimeError("call capture() first")
         self._sx.copy_(x, non_blocking=True)
         self._sy.copy_(y_true, non_blocking=True)
+        return self._graph_replay_only()
+
+    def _graph_replay_only(self) -> torch.Tensor:
+        """Replay on whatever the static input buffers hold."""
         if len(self._graph) == 1:
             self._graph[0].replay()
         else:
