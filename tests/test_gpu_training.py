@@ -473,3 +473,64 @@ def test_conv_bias_gradient_matches_autograd(lq):
         (conv2d_nhwc(x, k, strides, pad) + b).square().sum().backward()
         for g, t in zip(got, (x, k, b)):
             assert float((g - t.grad).abs().max()) <= 1e-4 * float(t.grad.abs().max())
+
+
+# ------------------------------------------------------------------ BASELINE configs[0]: the MNIST model, step by step
+def test_mnist_training_steps_follow_the_oracle(lq):
+    """MNIST/nested_quantization_layer/experiment.py:121-173,303-305 restated in numpy on top of the oracle
+    (fake-quant forward, nested backward, Keras Adam, MinValueConstraint) against TrainStep, three steps:
+    the quantised forward is bit-exact, so the trajectories differ only by matmul / softmax rounding."""
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training import models
+    from learned_quantization_b200.training.step import TrainStep
+    lam, lr, B = 1e-10, 1e-3, 32
+    torch.manual_seed(4)
+    net = models.mnist_mlp(lam, seed=42, orientation="rowwise").cuda()
+    x, y = models.synthetic_batch(B, (28, 28, 1), "cuda", seed=5)
+    x = x / 255.0
+    net(x)
+    rng = np.random.default_rng(6)
+    with torch.no_grad():
+        for q in (net.d1.nested_q_w_layer, net.d1.nested_q_b_layer, net.d2.nested_q_w_layer, net.d2.nested_q_b_layer):
+            q.scale.copy_(dev(rng.uniform(2e-3, 8e-3, tuple(q.scale.shape)).astype(np.float32)))
+        net.d1.b.copy_(dev(rng.normal(0, 0.05, 128).astype(np.float32)))
+        net.d2.b.copy_(dev(rng.normal(0, 0.05, 10).astype(np.float32)))
+    names = ["W1", "b1", "W2", "b2"]
+    P = dict(zip(names, (t.detach().cpu().numpy().copy() for t in (net.d1.W, net.d1.b, net.d2.W, net.d2.b))))
+    S = dict(zip(names, (q.scale.detach().cpu().numpy().copy() for q in
+                         (net.d1.nested_q_w_layer, net.d1.nested_q_b_layer, net.d2.nested_q_w_layer, net.d2.nested_q_b_layer))))
+    mP = {k: np.zeros_like(v) for k, v in P.items()}; vP = {k: np.zeros_like(v) for k, v in P.items()}
+    mS = {k: np.zeros_like(v) for k, v in S.items()}; vS = {k: np.zeros_like(v) for k, v in S.items()}
+    X = x.flatten(1).cpu().numpy().astype(np.float32)
+    Y = y.cpu().numpy()
+    step = TrainStep(net, scce, optimizer="adam", lr=lr)
+    for it in range(1, 4):
+        # ---- oracle step
+        Q = {k: o.fq_forward(P[k], S[k]) for k in names}                       # (codes, fake-quantised)
+        yq = {k: Q[k][1] for k in names}
+        h = X @ yq["W1"] + yq["b1"]
+        a = np.maximum(h, 0)
+        z = a @ yq["W2"] + yq["b2"]
+        e = np.exp(z - z.max(axis=1, keepdims=True)); p = e / e.sum(axis=1, keepdims=True)
+        loss_ref = float(np.mean(-np.log(np.clip(p[np.arange(B), Y], 1e-7, 1 - 1e-7))))
+        dz = p.copy(); dz[np.arange(B), Y] -= 1; dz = (dz / B).astype(np.float32)
+        g = {"W2": a.T @ dz, "b2": dz.sum(0)}
+        dh = (dz @ yq["W2"].T) * (h > 0)
+        g["W1"], g["b1"] = X.T @ dh, dh.sum(0)
+        for k in names:
+            gk = g[k].astype(np.float32)
+            _, ds = o.nested_backward(gk, Q[k][0], Q[k][1], S[k], lam, accum="fp64")
+            P[k], mP[k], vP[k] = o.adam_step(P[k], gk, mP[k], vP[k], lr, it)
+            S[k], mS[k], vS[k] = o.adam_step(S[k], np.asarray(ds, np.float32).reshape(S[k].shape), mS[k], vS[k], lr, it,
+                                             min_value=o.SCALE_INIT)
+        # ---- our step
+        loss = float(step(x, y))
+        assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref), (it, loss, loss_ref)
+        got_P = dict(zip(names, (t.detach().cpu().numpy() for t in (net.d1.W, net.d1.b, net.d2.W, net.d2.b))))
+        got_S = dict(zip(names, (q.scale.detach().cpu().numpy() for q in
+                                 (net.d1.nested_q_w_layer, net.d1.nested_q_b_layer, net.d2.nested_q_w_layer, net.d2.nested_q_b_layer))))
+        for k in names:
+            # Adam's first steps move every weight by ~lr whatever the gradient's size: compare on that scale
+            assert float(np.max(np.abs(got_P[k] - P[k]))) <= 0.02 * lr, (it, k)
+            assert float(np.max(np.abs(got_S[k] - S[k]))) <= 0.02 * lr, (it, k)
