@@ -179,7 +179,7 @@ class TrainStep:
         exact.  Single device: ONE graph for the whole step.  Data parallel: three graphs
         (forward+backward | scale backward | update) with the NCCL collective launched between them
         from the host -- capturing the collective itself deadlocked at replay on this stack
-        (NCCL 2.28.9, 2 x B200), so it stays outside.
+        (NCCL 2.28.9, 2 x B200; global and thread-local capture modes alike), so it stays outside.
         `x`, `y_true` fix the static input shapes; replay() copies new batches into them."""
         self._sx, self._sy = x.clone(), y_true.clone()
         side = torch.cuda.Stream()
