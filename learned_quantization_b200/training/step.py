@@ -126,6 +126,11 @@ class TrainStep:
         self._graph = None
 
     def _scale_backward(self):
+        if self.bank.sgrad_mode == _lib.LQ_SGRAD_NONE:
+            # CL:61-62 / PI:62-64: the operator's scale gradient is zeros -- one fill of the bucket's tail
+            # instead of one per tensor
+            self.bucket.flat[self.bucket.n_exact:self.bucket.n_total].zero_()
+            return
         self.bank.backward(self.bucket.dy, self.bucket.ds)
 
     # The step in three pieces, so that the collective can stay outside a CUDA graph:
