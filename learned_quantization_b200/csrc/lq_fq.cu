@@ -269,11 +269,16 @@ __device__ __forceinline__ void finish_group_value(const FinJob& f, long long g,
   f.ds[g] = __fmul_rn(mean, mx);
 }
 
+// WPG = warps per group: 1 (eight groups per block) when a group has at most 256 partials, 8 (one
+// block per group) above that -- a per-tensor scale on a 4 Mi-element tensor has 2048 partials in its
+// single group, which one warp would walk in 16 dependent trips.
+template <int WPG>
 __global__ void __launch_bounds__(256) finalize_warp_kernel(const __grid_constant__ FinJob f) {
   cudaGridDependencySynchronize();
-  const long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long g = (WPG == 1) ? (long long)blockIdx.x * 8 + warp : (long long)blockIdx.x;
   if (g >= f.C) return;
-  const int lane = threadIdx.x & 31;
+  const int sub = (WPG == 1) ? 0 : warp;                   // which slice of the group's partials this warp folds
   const long long K = partials_per_group(f);
   double sum = 0.0;
   unsigned long long cnt = 0ull;
@@ -282,11 +287,11 @@ __global__ void __launch_bounds__(256) finalize_warp_kernel(const __grid_constan
   // simple layouts: partial k of group g sits at base + k * stride
   const long long stride = (f.regime == REG_ROW) ? f.C : (f.regime == REG_COL ? f.W : 1);
   const float4* base = f.part + ((f.regime == REG_LIN) ? g * f.nlin : g);
-  for (long long k0 = lane; k0 < K; k0 += 128) {
+  for (long long k0 = sub * 32 + lane; k0 < K; k0 += 128ll * WPG) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long k = k0 + 32 * u;
+      const long long k = k0 + 32ll * WPG * u;
       v[u] = (k < K) ? (simple ? base[k * stride] : f.part[partial_index(f, g, k)]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -300,7 +305,21 @@ __global__ void __launch_bounds__(256) finalize_warp_kernel(const __grid_constan
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
-  if (lane == 0) finish_group_value(f, g, sum, cnt, mx);
+  if (WPG == 1) {
+    if (lane == 0) finish_group_value(f, g, sum, cnt, mx);
+    return;
+  }
+  __shared__ double ssum[8];
+  __shared__ unsigned long long scnt[8];
+  __shared__ float smx[8];
+  if (lane == 0) { ssum[warp] = sum; scnt[warp] = cnt; smx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sum = ssum[0]; cnt = scnt[0]; mx = smx[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { sum += ssum[i]; cnt += scnt[i]; mx = fmaxf(mx, smx[i]); }
+    finish_group_value(f, g, sum, cnt, mx);
+  }
 }
 
 __global__ void __launch_bounds__(kFinThreads) mt_finalize_kernel(const __grid_constant__ FinTable tab) {
@@ -400,7 +419,10 @@ int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float
     if (rc) return rc;
     f.part = f.lin; f.regime = REG_LIN;
   }
-  return launch_after(finalize_warp_kernel, dim3((unsigned)((g.C + 7) / 8)), dim3(256), st, "finalize launch", f);
+  const long long K = f.regime == REG_LIN ? f.nlin : g.kper;
+  if (K > 256)
+    return launch_after(finalize_warp_kernel<8>, dim3((unsigned)g.C), dim3(256), st, "finalize launch", f);
+  return launch_after(finalize_warp_kernel<1>, dim3((unsigned)((g.C + 7) / 8)), dim3(256), st, "finalize launch", f);
 }
 
 int check_blocks(const Geom& g) {
