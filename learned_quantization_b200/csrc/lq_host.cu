@@ -158,7 +158,10 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
     float* dY = stage_ptr(slot, 2);
     LQ_TRY(cudaMemcpyAsync(dP, hP + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D P");
     LQ_TRY(cudaMemcpyAsync(ddy, hdy + e0, (size_t)ne * 4, cudaMemcpyHostToDevice, st[slot]), "H2D dy");
-    const Geom g = make_geom(co, cc, ci, ci >= kRowMinInner, (p.mode == 0 && G.regime == REG_COL) ? G.rpc : 0);
+    // every slice keeps one segmentation: the whole tensor's (modes 0, 2) or that of a full group chunk (mode 1)
+    const int seg_of_slices = (G.regime != REG_ROW) ? 0
+        : (p.mode == 1 ? make_geom(1, p.step, inner, inner >= kRowMinInner).seg : G.seg);
+    const Geom g = make_geom(co, cc, ci, ci >= kRowMinInner, (p.mode == 0 && G.regime == REG_COL) ? G.rpc : 0, seg_of_slices);
     LQ_TRY_RC(fq_fwd_launch(g, dP, s_ptr, dY, nullptr, 0, qm, st[slot]));
     LQ_TRY_RC(fq_bwd_elements_launch(g, ddy, dP, s_ptr, penalty_threshold, nullptr, part_ptr, qm, st[slot]));
     LQ_TRY(cudaMemcpyAsync(hy + e0, dY, (size_t)ne * 4, cudaMemcpyDeviceToHost, st[slot]), "D2H y");
