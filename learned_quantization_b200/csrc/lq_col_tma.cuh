@@ -24,7 +24,10 @@
 
 namespace lq {
 
-constexpr int kTmaStages = 3;
+#ifndef LQ_TMA_STAGES
+#define LQ_TMA_STAGES 3
+#endif
+constexpr int kTmaStages = LQ_TMA_STAGES;
 constexpr int kTmaRowsPerThread = 8;
 constexpr int kTmaTileFloats = kTmaRowsPerThread * kThreads;   // 2048 floats = 8 KB per array per stage
 
