@@ -398,12 +398,6 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   }
 }
 
-template <class Op, bool STREAM, bool VEC>
-__device__ __forceinline__ void run_job(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue) {
-  if (j.regime == REG_ROW) run_row<Op, STREAM, VEC>(j, blk, op, queue);
-  else run_col<Op, STREAM, VEC>(j, blk, op, smem, queue);
-}
-
 // Single-tensor kernels: the Job travels in the kernel parameters.  One instantiation per
 // regime so that each keeps only its own registers (the ROW kernel is the bandwidth path).
 template <class Op>
