@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LQ_LIBRARY") or os.path.join(_HERE, "csrc", "liblq.so")
 
 LQ_OK = 0
+LQ_E_NULLPTR, LQ_E_BADSHAPE, LQ_E_BADMODE, LQ_E_WORKSPACE, LQ_E_CUDA, LQ_E_NCCL = -1, -2, -3, -4, -5, -6
 LQ_ROUND_FLOOR, LQ_ROUND_RNE = 0, 1
 LQ_CODES_NONE, LQ_CODES_F32, LQ_CODES_I32, LQ_CODES_I8 = 0, 1, 2, 3
 LQ_PEN_MAXBIN, LQ_PEN_DIFFERENCE, LQ_PEN_INVERSE = 0, 1, 2

@@ -118,9 +118,9 @@ class P2PFinish:
                 errs = [e for e in got2 if e]
             if errs:
                 self.close()
-                raise _lib.LqError(_lib.LQ_OK - 5, "peer-memory exchange unavailable: " + errs[0])
+                raise _lib.LqError(_lib.LQ_E_CUDA, "peer-memory exchange unavailable: " + errs[0])
         elif err:
-            raise _lib.LqError(_lib.LQ_OK - 5, err)
+            raise _lib.LqError(_lib.LQ_E_CUDA, err)
 
     def finish(self, local_stats: torch.Tensor, penalty_threshold: float, n_per_group: float, ds: torch.Tensor) -> torch.Tensor:
         if local_stats.dtype != torch.float64 or not local_stats.is_cuda or not local_stats.is_contiguous():
