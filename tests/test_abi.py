@@ -86,3 +86,17 @@ def test_product_has_no_cpu_path(pkg):
                 for line in open(os.path.join(dirpath, f)):
                     code = line.split("#")[0].split("//")[0]
                     assert not re.search(r"\b(import|from|include|dlopen|CDLL)\b.*oracle", code), (f, line)
+
+
+def test_header_is_plain_c_and_the_c_demo_links(pkg, tmp_path):
+    """include/lq.h compiles as C (not just C++) and a C program links against liblq.so without Python."""
+    import shutil
+    import subprocess
+    if not (shutil.which("gcc") and os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    exe = tmp_path / "lq_demo"
+    cmd = ["gcc", "-O1", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           os.path.join(ROOT, "examples", "lq_demo.c"), "-o", str(exe),
+           "-L" + os.path.dirname(pkg._lib.LIB_PATH), "-llq", "-L/usr/local/cuda/lib64", "-lcudart", "-lm"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
