@@ -1,0 +1,103 @@
+"""GPU tier, needs TWO devices (skipped on a single-GPU box; run with `gpurun --gpus 2`): data parallelism
+through our NCCL communicator.  Two ranks, each with half of a batch, must end a training step where one
+device with the whole batch ends it (exact mode: allreduce dy, threshold backward on the averaged dy)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LR, STEPS, B = 1e-3, 2, 8
+
+
+def _net():
+    from learned_quantization_b200 import RandomNormal
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            init = RandomNormal(seed=9)
+            self.c1 = nq.CustomConv2DLayer(seed=9, penalty_threshold=1e-3, orientation="channelwise", initializer=init,
+                                           filters=8, kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
+                                           regularizer=None, kernel_storage="ohwi")
+            self.fc = nq.CustomDenseLayer(seed=9, units=10, penalty_threshold=1e-3, orientation="rowwise", initializer=init,
+                                          name="fc", regularizer=None)
+
+        def forward(self, x):
+            return torch.softmax(self.fc(torch.relu(self.c1(x)).mean(dim=(1, 2))), dim=-1)
+    return Net()
+
+
+def _prepare(net, x):
+    net(x[:1])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    with torch.no_grad():
+        for q in (net.c1.nested_q_k_layer, net.c1.nested_q_b_layer, net.fc.nested_q_w_layer, net.fc.nested_q_b_layer):
+            q.scale.copy_(torch.empty_like(q.scale).uniform_(5e-3, 2e-2, generator=g))
+
+
+def _data():
+    g = torch.Generator().manual_seed(11)
+    return torch.rand(B, 10, 10, 3, generator=g), torch.randint(0, 10, (B,), generator=g)
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training.dp import NcclComm
+    from learned_quantization_b200.training.step import TrainStep
+    torch.manual_seed(0)
+    x, y = _data()
+    x, y = x.cuda(), y.cuda()
+    net = _net().cuda()
+    _prepare(net, x)
+    comm = NcclComm()
+    step = TrainStep(net, scce, optimizer="adam", lr=LR, comm=comm, ds_mode="exact")
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    for _ in range(STEPS):
+        step(x[lo:hi], y[lo:hi])
+    torch.cuda.synchronize()
+    params = [p.detach().cpu().numpy().copy() for p in net.parameters()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, params)
+    if rank == 0:
+        for a, b in zip(gathered[0], gathered[1]):
+            assert np.array_equal(a, b), "ranks diverged: exact mode must leave bit-identical parameters everywhere"
+        np.savez(out_path, *params)
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_device_on_the_whole_batch(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dp.npz")
+    mp.spawn(_worker, args=(2, 29671, out), nprocs=2, join=True)
+    got = np.load(out)
+    # the same two steps on one device with the whole batch
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.training.step import TrainStep
+    torch.cuda.set_device(0)
+    torch.manual_seed(0)
+    x, y = _data()
+    x, y = x.cuda(), y.cuda()
+    net = _net().cuda()
+    _prepare(net, x)
+    step = TrainStep(net, scce, optimizer="adam", lr=LR)
+    for _ in range(STEPS):
+        step(x, y)
+    for i, p in enumerate(net.parameters()):
+        want = p.detach().cpu().numpy()
+        assert float(np.max(np.abs(got[f"arr_{i}"] - want))) <= 0.02 * LR, i
