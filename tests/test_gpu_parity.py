@@ -571,3 +571,67 @@ def test_full_size_64mi_vs_oracle(lq, layout):
     assert bits_equal(host(y).reshape(shape), y_ref)
     _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, 1e-3, accum="fp64")
     assert ds_close(host(ds).reshape(ds_ref.shape), ds_ref)
+
+
+# ------------------------------------------------------------------ beyond 32-bit element indices
+@pytest.mark.parametrize("layout", [(1, 1, (1 << 31) + 12345), (5, 1024, 1 << 19), (5 << 24, 32, 1)])
+def test_more_than_2_pow_31_elements(lq, layout):
+    """Maximum sizes: tensors whose element (and byte) offsets do not fit 32 bits, in each traversal regime.
+    Size-independent properties: the forward of the whole tensor equals, bit for bit, the forward of
+    independent pieces of it (each below 2^31 elements, the range the oracle tests cover) and the oracle on
+    windows at the start, across the 2^31-element / 2^32-byte marks and at the ragged end; the scale gradient
+    of the whole tensor equals statistics of the pieces + finish."""
+    ops = lq.ops
+    outer, C, inner = layout
+    n = outer * C * inner
+    free, _ = torch.cuda.mem_get_info()
+    if free < 5 * 4 * n + (4 << 30):
+        pytest.skip("not enough free device memory")
+    lam = 1e-3
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Pd = torch.empty(n, device="cuda")
+    dyd = torch.empty(n, device="cuda")
+    step = 1 << 28
+    for a in range(0, n, step):                                   # generate piecewise: bounded temporaries
+        b = min(n, a + step)
+        Pd[a:b] = torch.randn(b - a, device="cuda", generator=g) * 0.05
+        dyd[a:b] = torch.randn(b - a, device="cuda", generator=g) * 1e-3
+    sd = torch.rand(C, device="cuda", generator=g) * 1.5e-2 + 5e-3
+    y = ops.fq_fwd(Pd, sd, layout)
+    dX, ds = ops.fq_bwd_threshold(dyd, Pd, sd, lam, layout, write_dx=True)
+    torch.cuda.synchronize()
+
+    # pieces: along `outer` when there is one, along the flat index for the per-tensor layout
+    if C == 1:
+        cuts = [0, (1 << 30) + 4, n]
+        piece = lambda a, b: (1, 1, b - a)
+        span = lambda a, b: (a, b)
+    else:
+        cuts = [0, outer // 2, outer]
+        piece = lambda a, b: (b - a, C, inner)
+        span = lambda a, b: (a * C * inner, b * C * inner)
+    stats = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        lo, hi = span(a, b)
+        assert hi - lo < (1 << 31)
+        y_piece = ops.fq_fwd(Pd[lo:hi], sd, piece(a, b))
+        assert torch.equal(y_piece.view(torch.int32), y[lo:hi].view(torch.int32)), (a, b)
+        del y_piece
+        _, st = ops.fq_bwd_threshold_stats(dyd[lo:hi], Pd[lo:hi], sd, lam, piece(a, b))
+        stats.append(st)
+    assert torch.equal(dX.view(torch.int32), dyd.view(torch.int32))
+    ds_pieces = ops.fq_bwd_threshold_finish(torch.stack(stats).contiguous(), lam, n // C)
+    assert ds_close(host(ds).reshape(-1), host(ds_pieces).reshape(-1), tol=1e-6)
+
+    # oracle on windows (whole groups rows for the grouped layouts)
+    row = C * inner if C > 1 and inner < 128 else 1
+    marks = [0, (1 << 30), (1 << 31), n]
+    w = 1 << 16
+    for m in marks:
+        lo = max(0, min(n - w, m - w // 2))
+        lo -= lo % (row if row > 1 else 4)
+        hi = min(n, lo + w) if m != n else n
+        idx = torch.arange(lo, hi, device="cuda")
+        grp = host(((idx // inner) % C).to(torch.int32))
+        _, y_ref = o.fq_forward(host(Pd[lo:hi]), host(sd)[grp])
+        assert bits_equal(host(y[lo:hi]), y_ref), m
