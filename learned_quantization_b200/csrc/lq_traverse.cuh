@@ -316,57 +316,88 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   // 64 registers and halve the resident warps.  (The threshold backward does not come here: it takes
   // run_col1 or the TMA-staged kernel.)
   constexpr int U = (Op::kIn2 && Op::kReduce) ? 2 : 4;
-  const long long step = j.by;
-  auto load = [&](long long rb, float (&p)[U][V], float (&d)[U][V]) {
+  // Addresses: one pointer per array, advanced by a constant stride (the per-row 64-bit multiply of
+  // row * W + column and its bound check used to be a third of the instruction stream); rows are
+  // counted, not compared: this thread owns rows r0+ty, r0+ty+by, ... (rows_mine of them).
+  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);                       // block-uniform trips
+  const int rows_mine = active ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
+  const long long stride = (long long)j.by * j.W;
+  const long long base = active ? (r0 + ty) * j.W + col0 : 0;
+  const float* Pp = j.P + base;
+  const float* Dp = Op::kIn2 ? j.dy + base : nullptr;
+  float* Op_ = out + base;
+  // A full trip of four rows hands each of the thread's columns to the operator as one quad (four
+  // elements of ONE group: one range guard, one branch), exactly like a ROW thread's 16 bytes.
+  constexpr bool kQuads = (U == 4) && (V == 4) && (Op::kDeferSlots == 0);
+
+#pragma unroll 1
+  for (int i0 = 0; i0 < rows_blk; i0 += U) {
+    float p[U][V], d[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long rr = rb + ty + u * step;
-      if (active && rr < r1) {
-        const long long e = rr * j.W + col0;
+      if (i0 + u < rows_mine) {
         if constexpr (VEC) {
-          const float4 pv = ld4<STREAM>(reinterpret_cast<const float4*>(j.P + e));
+          const float4 pv = ld4<STREAM>(reinterpret_cast<const float4*>(Pp + u * stride));
           p[u][0] = pv.x; p[u][1] = pv.y; p[u][2] = pv.z; p[u][3] = pv.w;
           if (Op::kIn2) {
-            const float4 dv = ld4<STREAM>(reinterpret_cast<const float4*>(j.dy + e));
+            const float4 dv = ld4<STREAM>(reinterpret_cast<const float4*>(Dp + u * stride));
             d[u][0] = dv.x; d[u][1] = dv.y; d[u][2] = dv.z; d[u][3] = dv.w;
           }
         } else {
-          p[u][0] = ld1<STREAM>(j.P + e);
-          if (Op::kIn2) d[u][0] = ld1<STREAM>(j.dy + e);
+          p[u][0] = ld1<STREAM>(Pp + u * stride);
+          if (Op::kIn2) d[u][0] = ld1<STREAM>(Dp + u * stride);
         }
       }
     }
-  };
-  auto compute = [&](long long rb, float (&p)[U][V], float (&d)[U][V]) {
+    bool done = false;
+    if constexpr (kQuads) {
+      if (i0 + U <= rows_mine) {
+        float o[U][V], c[U][V];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long rr = rb + ty + u * step;
-      if (active && rr < r1) {
-        const long long e = rr * j.W + col0;
-        float o[V], c[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-          op.elem_k(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc, k, o[k], c[k], df);
-        if (wr) {
-          if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(out + e), make_float4(o[0], o[1], o[2], o[3]));
-          else st1<STREAM>(out + e, o[0]);
+        for (int k = 0; k < V; ++k) {
+          float4 oq, cq;
+          op.quad(make_float4(p[0][k], p[1][k], p[2][k], p[3][k]),
+                  Op::kIn2 ? make_float4(d[0][k], d[1][k], d[2][k], d[3][k]) : make_float4(0.f, 0.f, 0.f, 0.f),
+                  ctx[k], j, acc[k], oq, cq, df);
+          o[0][k] = oq.x; o[1][k] = oq.y; o[2][k] = oq.z; o[3][k] = oq.w;
+          c[0][k] = cq.x; c[1][k] = cq.y; c[2][k] = cq.z; c[3][k] = cq.w;
         }
-        if (Op::kCodes && j.codes) {
 #pragma unroll
-          for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+        for (int u = 0; u < U; ++u) {
+          if (wr) st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
+          if (Op::kCodes && j.codes) {
+            const long long e = base + (long long)(i0 + u) * stride;
+#pragma unroll
+            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[u][k]);
+          }
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u < rows_mine) {
+          float o[V], c[V];
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            op.elem_k(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc, k, o[k], c[k], df);
+          if (wr) {
+            if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(o[0], o[1], o[2], o[3]));
+            else st1<STREAM>(Op_ + u * stride, o[0]);
+          }
+          if (Op::kCodes && j.codes) {
+            const long long e = base + (long long)(i0 + u) * stride;
+#pragma unroll
+            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+          }
         }
       }
     }
-    if (Op::kDeferSlots) op.flush_k(acc, df);
-  };
-  {
-    const long long trip = U * step;
-    float pa[U][V], da[U][V];
-#pragma unroll 1
-    for (long long rb = r0; rb < r1; rb += trip) {
-      load(rb, pa, da);
-      compute(rb, pa, da);
-    }
+    if (Op::kDeferSlots) op.flush_k(acc, df);     // block-uniform trip count: the warp is converged
+    Pp += U * stride;
+    if (Op::kIn2) Dp += U * stride;
+    Op_ += U * stride;
   }
 
   if (Op::kReduce) {
@@ -400,6 +431,12 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 
 // Single-tensor kernels: the Job travels in the kernel parameters.  One instantiation per
 // regime so that each keeps only its own registers (the ROW kernel is the bandwidth path).
+// COL kernels of the light operators are held to 64 registers (four blocks per SM): grids of ~3.5 blocks
+// per SM (a 4 Mi-element tensor) otherwise need a second wave.  The two-input operators keep
+// what they need (they carry per-thread state for the rare path / four groups).
+template <class Op>
+constexpr int kColMinBlocks = Op::kIn2 ? 1 : 4;
+
 template <class Op>
 struct SmemPlan {
   static constexpr int kQueueEntries = Op::kDeferSlots ? Op::kDeferSlots * kThreads : 1;
@@ -414,7 +451,7 @@ __global__ void __launch_bounds__(kThreads) row_kernel(const __grid_constant__ J
   run_row<Op, STREAM, VEC>(j, blockIdx.x, op, queue);
 }
 template <class Op, bool STREAM, bool VEC>
-__global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ Job j, const Op op) {
+__global__ void __launch_bounds__(kThreads, kColMinBlocks<Op>) col_kernel(const __grid_constant__ Job j, const Op op) {
   __shared__ Acc smem[SmemPlan<Op>::kColEntries];
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
   cudaGridDependencySynchronize();
@@ -425,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) col_kernel(const __grid_constant__ J
 // regime (a launch holds the ROW tensors or the COL tensors of a step, never both), so that the ROW
 // units keep the ROW kernel's register budget: the combined kernel needed 114 registers.
 template <class Op, int REGIME>
-__global__ void __launch_bounds__(kThreads) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
+__global__ void __launch_bounds__(kThreads, REGIME == REG_COL ? kColMinBlocks<Op> : 1) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
   __shared__ Acc smem[REGIME == REG_COL ? SmemPlan<Op>::kColEntries : 1];
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
   int lo = 0, hi = tab.n - 1;
