@@ -47,7 +47,14 @@ struct MaxBinStatOp : OpBase<MaxBinStatOp> {
       d.x = __fdiv_rn(fabsf(p.x), c.rc.s); d.y = __fdiv_rn(fabsf(p.y), c.rc.s);
       d.z = __fdiv_rn(fabsf(p.z), c.rc.s); d.w = __fdiv_rn(fabsf(p.w), c.rc.s);
     }
-    take(d.x, acc); take(d.y, acc); take(d.z, acc); take(d.w, acc);
+    // four at once: the new maximum first, then the ties with it (the count of elements equal to the final
+    // maximum does not depend on the order they were seen in); NaNs drop out of fmaxf and of == alike
+    const float m4 = fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w));
+    const float mx = fmaxf(acc.c, m4);
+    unsigned cnt = (m4 > acc.c) ? 0u : acc.b;
+    cnt += (d.x == mx) ? 1u : 0u; cnt += (d.y == mx) ? 1u : 0u;
+    cnt += (d.z == mx) ? 1u : 0u; cnt += (d.w == mx) ? 1u : 0u;
+    acc.b = cnt; acc.c = mx;
   }
 };
 
@@ -198,11 +205,25 @@ __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g)
   double sum = 0.0;
   float mx = -1.f;
   unsigned long long ties = 0ull;
-  for (long long k = threadIdx.x; k < K; k += kFinThreads) {
-    const float4 v = f.part[partial_index(f, g, k)];
-    sum += (double)v.x;
-    const unsigned long long b = __float_as_uint(v.y);
-    if (v.z > mx) { mx = v.z; ties = b; } else if (v.z == mx) ties += b;
+  // four independent 16-byte loads per thread per trip, and no 64-bit division on the layouts whose
+  // partials sit at a constant stride (one load at a time behind partial_index() cost 17 us for the
+  // 2048 partials per group of an interleaved 64 Mi tensor); thread t still folds t, t+128, ... in order
+  const bool simple = (f.regime == REG_ROW && f.nseg == 1) || f.regime == REG_LIN || (f.regime == REG_COL && f.inner == 1);
+  const long long stride = (f.regime == REG_ROW) ? f.C : (f.regime == REG_COL ? f.W : 1);
+  const float4* base = f.part + ((f.regime == REG_LIN) ? g * f.nlin : g);
+  for (long long k0 = threadIdx.x; k0 < K; k0 += 4 * kFinThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long k = k0 + (long long)u * kFinThreads;
+      v[u] = (k < K) ? (simple ? base[k * stride] : f.part[partial_index(f, g, k)]) : make_float4(0.f, 0.f, -2.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sum += (double)v[u].x;
+      const unsigned long long b = __float_as_uint(v[u].y);
+      if (v[u].z > mx) { mx = v[u].z; ties = b; } else if (v[u].z == mx) ties += b;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
