@@ -28,6 +28,9 @@ namespace lq {
 #define LQ_TMA_STAGES 3
 #endif
 constexpr int kTmaStages = LQ_TMA_STAGES;
+#ifndef LQ_TMA_BPS
+#define LQ_TMA_BPS 8
+#endif
 constexpr int kTmaRowsPerThread = 8;
 constexpr int kTmaTileFloats = kTmaRowsPerThread * kThreads;   // 2048 floats = 8 KB per array per stage
 
@@ -189,7 +192,7 @@ inline Geom make_col_tma_geom(long long outer, long long C, long long inner) {
   const int tc = g.W >= 128 ? 128 : (g.W >= 64 ? 64 : 32);
   const long long ncolblk = cdiv(g.W, tc);
   const int tile_rows = kTmaRowsPerThread * (kThreads / tc);
-  long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * 8), tile_rows) * tile_rows;   // ~8 blocks per SM
+  long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * LQ_TMA_BPS), tile_rows) * tile_rows;   // ~LQ_TMA_BPS blocks per SM
   if (rpc < 4ll * tile_rows) rpc = 4ll * tile_rows;
   if (rpc > 8192) rpc = 8192 / tile_rows * tile_rows;
   g.bx = tc; g.by = kThreads / tc;
