@@ -543,11 +543,23 @@ def sweep_layouts():
     for lg in (20, 22, 24, 26, 28, 30):
         n = 1 << lg
         out.append(("per_tensor", (1, 1, n)))
-        for c in (64, 512, 2048):
+        for c in (64, 256, 512, 2048):
             if n // (512 * c) >= 1:
                 out.append((f"hwio_like_C{c}", (n // (512 * c), c, 512)))
             out.append((f"rows_C{c}", (1, c, n // c)))
             out.append((f"interleaved_C{c}", (n // c, c, 1)))
+    return [(name, layout, "trained", LAMBDA) for name, layout in out] + sweep_variants()
+
+
+def sweep_variants():
+    """SURVEY 8d's other operating points, at the headline size only: scales at their initial value
+    100*eps (codes ~ +-2e4, nothing below the threshold) and the reference's own lambdas (0, 1e-11, 1e-10:
+    every element above the threshold, the all-above branch NQ:77-79 / 103-105)."""
+    n = 1 << 26
+    base = [("per_tensor", (1, 1, n)), ("hwio_like_C512", (n // (512 * 512), 512, 512)), ("interleaved_C512", (n // 512, 512, 1))]
+    out = [(name, layout, "init", LAMBDA) for name, layout in base]
+    for lam in (0.0, 1e-11, 1e-10):
+        out += [(name, layout, "trained", lam) for name, layout in base]
     return out
 
 
@@ -564,12 +576,15 @@ def run_sweep(args):
     peak, _ = measured_peak()
     gen = torch.Generator(device="cuda").manual_seed(42)
     only = set(args.only.split(",")) if args.only else None
-    for name, layout in sweep_layouts():
+    for name, layout, scales, lam in sweep_layouts():
         n = layout[0] * layout[1] * layout[2]
         if n > args.max_elems or (only and name not in only):
             continue
         nsets = max(2, min(16, -(-(600 << 20) // (12 * n))))
-        s = torch.empty(layout[1], device="cuda").uniform_(5e-3, 2e-2, generator=gen)
+        if scales == "trained":
+            s = torch.empty(layout[1], device="cuda").uniform_(5e-3, 2e-2, generator=gen)
+        else:
+            s = torch.full((layout[1],), 1.1920928955078125e-05, device="cuda")        # NQ:156-158
         Ps = [torch.empty(n, device="cuda").normal_(0, 0.05, generator=gen) for _ in range(nsets)]
         dys = [torch.empty(n, device="cuda").normal_(0, 1e-3, generator=gen) for _ in range(nsets)]
         outs = [torch.empty(n, device="cuda") for _ in range(nsets)]
@@ -582,7 +597,7 @@ def run_sweep(args):
                                 torch.cuda.current_stream().cuda_stream))
 
         def bwd(i):
-            check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), LAMBDA, outs[i].data_ptr(),
+            check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), lam, outs[i].data_ptr(),
                                           ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(),
                                           torch.cuda.current_stream().cuda_stream))
 
@@ -615,7 +630,8 @@ def run_sweep(args):
                 ts = sorted(a.elapsed_time(b) for a, b in evs)
                 res[tag] = ts[len(ts) // 2]
         gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
-        print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "rotating_sets": nsets,
+        print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "scales": scales, "lambda": lam,
+                          "rotating_sets": nsets,
                           "timing": f"CUDA graph of {args.steps} launches" if graphed else "per-launch CUDA events",
                           "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
                           "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),

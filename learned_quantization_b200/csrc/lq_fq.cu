@@ -162,7 +162,10 @@ static BwdThresholdOp<EXT> make_bwd_op(const QMode& qm, float lam) {
   BwdThresholdOp<EXT> op;
   op.qm = qm; op.lam = lam;
   op.lam_hi = (float)((double)lam * (1.0 + 1.0 / 1048576.0));     // >= lam*(1+2^-21) after the fp32 rounding
-  op.lam_fast = (lam >= 8.673617379884035e-19f /*2^-60*/ && lam <= 1.152921504606847e+18f /*2^60*/) ? 1 : 0;
+  // lam == 0 (a reference operating point: every finite ratio is "above") is safe too: lam_hi is then 0,
+  // |nz| * 0 is 0 for every finite nz (NaN for an infinite or NaN one, which sends the element to the exact
+  // path), and |dy| >= 0 fails only for a NaN dy.  Only a TINY non-zero lam could underflow the product.
+  op.lam_fast = (lam == 0.0f || (lam >= 8.673617379884035e-19f /*2^-60*/ && lam <= 1.152921504606847e+18f /*2^60*/)) ? 1 : 0;
   op.lam_small = (lam > 0.0f && lam < 0.6f) ? 1 : 0;
   return op;
 }

@@ -395,6 +395,44 @@ def test_special_values(lq):
     assert np.isnan(ds_ref).all() and np.isnan(host(ds)).all()
 
 
+@pytest.mark.parametrize("lam", [0.0, -0.0, 1e-11, 1e-3])
+@pytest.mark.parametrize("shape,s_shape", [((4, 6, 256), (1, 6, 1)), ((1, 1, 4100), (1,)), ((2048, 40, 1), (1, 40, 1)),
+                                           ((16384, 64), (1, 64))])
+def test_special_gradients_at_every_lambda(lq, shape, s_shape, lam):
+    """lambda = 0 takes the filtered fast path (|dy| >= |nz| * 0): infinities, NaNs, zeros and denormals in dy,
+    zeros / infinities in y, in every traversal (ROW, register COL, TMA-staged COL) must come out as the oracle's."""
+    ops = lq.ops
+    rng = np.random.default_rng(77)
+    s = rng.uniform(5e-3, 2e-2, s_shape).astype(np.float32)
+    special_dy = np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-40, 3e38], np.float32)
+    for special_P in (np.array([0.0, -0.0, 1e-45, 1e-3], np.float32),                     # finite codes
+                      np.array([0.0, 1e-3, np.inf, -np.inf, 3e38], np.float32)):          # infinite codes too
+        P = rng.normal(0, 0.05, shape).astype(np.float32)
+        dy = rng.normal(0, 1e-3, shape).astype(np.float32)
+        flatP, flatd = P.reshape(-1), dy.reshape(-1)
+        n = flatP.size
+        idx = rng.choice(n, size=special_dy.size * special_P.size, replace=False)
+        k = 0
+        for a in special_dy:
+            for b in special_P:
+                flatd[idx[k]], flatP[idx[k]] = a, b
+                k += 1
+        for poison in (False, True):
+            if poison:
+                flatd[int(rng.integers(n))] = np.nan        # one NaN ratio: its group's ds becomes NaN, the others stay
+            with np.errstate(all="ignore"):
+                q_ref, y_ref = o.fq_forward(P, s)
+                _, ds_ref = o.nested_backward(dy, q_ref, y_ref, s, lam, accum="fp64")
+            dX, ds = ops.fq_bwd_threshold(dev(dy), dev(P), dev(s), lam, write_dx=True)
+            assert bits_equal(host(dX), dy)
+            got, want = host(ds).reshape(-1), ds_ref.reshape(-1)
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (lam, poison)
+            assert np.array_equal(np.isinf(got), np.isinf(want)) and np.array_equal(np.sign(got[np.isinf(got)]),
+                                                                                    np.sign(want[np.isinf(want)]))
+            ok = np.isfinite(want)
+            assert ds_close(got[ok], want[ok]), (lam, poison)
+
+
 def test_rne_clamp_extension(lq):
     from learned_quantization_b200 import _lib
     ops = lq.ops
