@@ -201,7 +201,7 @@ def run_ours(args):
     import learned_quantization_b200 as lq
     ops = lq.ops
     if args.only_qat:
-        q = run_qat(args, rank, world, local)
+        q = run_qat(args, rank, world, local, model=args.qat_model)
         if rank == 0:
             print(json.dumps(q))
         if world > 1:
@@ -396,26 +396,36 @@ def run_ours(args):
             p2p.close()
         comm.close()
         comm = None
-    qat = None
+    qat = qat_cifar = None
     if not args.no_qat:
         del sets, y, dX, hP, hdy, hy, hws
         torch.cuda.empty_cache()
         qat = run_qat(args, rank, world, local)
+        if world == 1:                     # BASELINE configs[1] is a single-GPU configuration
+            try:
+                qat_cifar = run_qat(args, rank, world, local, model="cifar_paper")
+            except Exception as e:         # reported, never allowed to take the headline line down
+                qat_cifar = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if qat is not None:
             line["qat"] = qat
+        if qat_cifar is not None:
+            line["qat_cifar_paper"] = qat_cifar
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------- QAT training step
-def run_qat(args, rank, world, local):
+def run_qat(args, rank, world, local, model="imagenette"):
     """Second half of BASELINE.json's metric: QAT images/s on the IMAGENETTE ResNet-style model
     (20 quantised convs + biases = 40 quantised tensors, nested variant, channelwise scales,
     lambda 1e-11, Adam 1e-4, 224x224x3, per-GPU batch 64 = the reference's batch), synthetic data.
     Data parallel: batch sharded, [dy | plain grads] mean-allreduced through lq_dp_allreduce
-    (our NCCL communicator), scale gradients in EXACT mode (training/dp.py).  Weak scaling."""
+    (our NCCL communicator), scale gradients in EXACT mode (training/dp.py).  Weak scaling.
+    model="cifar_paper": BASELINE configs[1] instead -- CIFAR-10/paper_implementation ResNet-18 on
+    CustomConv2DLayerNoBias + quantised fc (22 tensors, STE scale gradient PI:62-64, channelwise scales),
+    32x32x3, batch 256, SGD(0.1, momentum 0.9, nesterov, weight decay 5e-4) (experiment.py:130-141)."""
     import torch
     import torch.distributed as dist
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
@@ -427,13 +437,19 @@ def run_qat(args, rank, world, local):
     torch.backends.cudnn.allow_tf32 = True           # TF 2.11 enables TF32 convolutions by default too
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
-    batch, shape = args.qat_batch, (224, 224, 3)
+    cifar = model == "cifar_paper"
+    batch, shape = (256, (32, 32, 3)) if cifar else (args.qat_batch, (224, 224, 3))
     torch.manual_seed(42)
-    variant = args.qat_variant
-    value = 1e-11 if variant == "nested" else 1e-9       # lambda (nested) / gamma (custom loss), chapter4.tex
-    net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant,
-                                   kernel_storage=args.qat_storage).cuda().train()
+    variant = "paper" if cifar else args.qat_variant
+    value = 0.0 if cifar else (1e-11 if variant == "nested" else 1e-9)   # lambda (nested) / gamma (custom loss), chapter4.tex
+    if cifar:
+        net = models.cifar_resnet18(0.0, seed=42, orientation="channelwise").cuda().train()
+    else:
+        net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant,
+                                       kernel_storage=args.qat_storage).cuda().train()
     x, y = models.synthetic_batch(batch, shape, "cuda", seed=42 + rank)
+    if cifar:
+        x = x / 255.0
     with torch.no_grad():
         net(x[:2])                                    # builds the layers
     comm = NcclComm() if world > 1 else None
@@ -450,7 +466,12 @@ def run_qat(args, rank, world, local):
         loss_obj = cls(layers=hosts, penalty_rate=value, log_dir=tempfile.mkdtemp(prefix="lq_bench_"))
         loss_obj.log_to_files = False                 # the reference's three tf.print(file://) per step: not timed here
         loss_fn = loss_obj.compute_total_loss
-    step = TrainStep(net, loss_fn, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
+    if cifar:
+        logits_loss = lambda yt, logits: scce(yt, torch.softmax(logits, dim=-1))
+        step = TrainStep(net, logits_loss, optimizer="sgd", lr=0.1, momentum=0.9, nesterov=True, weight_decay=5e-4,
+                         comm=comm, ds_mode="exact")
+    else:
+        step = TrainStep(net, loss_fn, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
     hx = x.cpu().pin_memory()
     hy = y.cpu().pin_memory()
 
@@ -517,18 +538,22 @@ def run_qat(args, rank, world, local):
            "ms_per_step": dev_ms, "steps": steps, "warmup": warm,
            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
-           "config": {"workload": f"imagenette_resnet_{variant}_channelwise_224" + (f"_{args.qat_loss}" if variant == "custom_loss" else ""),
+           "config": {"workload": "cifar10_paper_resnet18_channelwise_32" if cifar else
+                      f"imagenette_resnet_{variant}_channelwise_224" + (f"_{args.qat_loss}" if variant == "custom_loss" else ""),
                       "per_gpu_batch": batch, "global_batch": batch * world,
-                      "optimizer": "adam(1e-4) fused with l2 + MinValueConstraint",
-                      ("lambda" if variant == "nested" else "gamma"): value,
+                      "optimizer": "sgd(0.1, 0.9, nesterov, weight decay 5e-4) fused with MinValueConstraint" if cifar else
+                      "adam(1e-4) fused with l2 + MinValueConstraint",
+                      ("lambda" if variant in ("nested", "paper") else "gamma"): value,
                       "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
-                      "scale_grad_mode": "exact (allreduce dy, then threshold backward on every rank)",
+                      "scale_grad_mode": "none (STE: dX = dy, ds = zeros, PI:62-64)" if cifar else
+                      "exact (allreduce dy, then threshold backward on every rank)",
                       "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}",
-                      "kernel_storage": args.qat_storage + (" (logical HWIO, cuDNN channels-last order in memory)"
-                                                            if args.qat_storage == "ohwi" else ""),
+                      "kernel_storage": "hwio" if cifar else
+                      args.qat_storage + (" (logical HWIO, cuDNN channels-last order in memory)" if args.qat_storage == "ohwi" else ""),
                       "launch": "eager" if args.qat_eager else "one CUDA graph per step"},
            "allreduce_floats": step.bucket.n_exact,
-           "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 2, "lq_opt_adam": -(-len(step.table.params) // 56),
+           "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 0 if cifar else 2,
+                                     ("lq_opt_sgd" if cifar else "lq_opt_adam"): -(-len(step.table.params) // 56),
                                      "lq_dp_allreduce": 1 if world > 1 else 0},
            "last_loss": loss_host}
     if comm is not None:
@@ -661,6 +686,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-qat", action="store_true", help="skip the QAT images/s section of the line")
     ap.add_argument("--only-qat", action="store_true", help="debug: run only the QAT section and print it")
+    ap.add_argument("--qat-model", default="imagenette", choices=["imagenette", "cifar_paper"],
+                    help="with --only-qat: which training configuration to time")
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)

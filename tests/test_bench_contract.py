@@ -43,4 +43,6 @@ def test_gpu_arm_line():
     assert d["gpu_launches"] == 3 * d["steps"] and d["n_gpus"] == 1 and d["scaling"] == "weak"
     assert d["cpu_baseline"]["kind"] == "port" and 0 < d["cpu_baseline"]["value"] < d["e2e"]["value"]
     assert d["qat"]["unit"] == "images/s" and d["qat"]["value"] > 0 and d["qat"]["e2e"]["h2d_bytes_per_step"] > 0
+    c = d["qat_cifar_paper"]                     # BASELINE configs[1]
+    assert "error" not in c and c["config"]["per_gpu_batch"] == 256 and c["value"] > 0
     assert d["value"] > 3000, "fwd+bwd below half of the HBM roofline: something is wrong with the build"
