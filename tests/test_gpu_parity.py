@@ -510,6 +510,47 @@ def test_penalties_random_vs_oracle(lq):
             assert float(np.max(np.abs(host(dss[i]).astype(np.float64).reshape(gs.shape) - gs))) <= TOL * max(float(np.max(np.abs(gs))), 1e-30), (kind, i)
 
 
+@pytest.mark.parametrize("shape,s_shape", [((8, 4, 512), (1, 4, 1)), ((1, 1, 6000), (1,)), ((1000, 64), (1, 64)),
+                                           ((520, 36), (1, 36)), ((300, 7), (1, 7))])
+def test_maxbin_ties_inside_and_across_quads(lq, shape, s_shape):
+    """reduce_max's gradient splits evenly among ties (LF:90-94 under TF autodiff).  The kernels count ties four
+    elements at a time: put equal maxima next to each other (one ROW quad / one column's consecutive rows), far
+    apart, and with opposite signs, in some groups only."""
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(5)
+    K = rng.normal(0, 0.05, size=shape).astype(np.float32)
+    flat = K.reshape(-1)
+    C = s_shape[1] if len(s_shape) > 1 else 1
+    inner = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    row = C * inner
+    top = np.float32(0.75)
+    if C == 1:
+        flat[[0, 1, 2, 3, 4, 2048, 5999]] = [top, -top, top, top, top, -top, top]
+    else:
+        for g in range(0, C, 2):                                   # every other group gets ties
+            base = g * inner
+            if inner > 1:
+                flat[base:base + 3] = [top, -top, top]             # one quad of the group's first row
+                flat[base + row * (shape[0] - 1) + inner - 1] = top    # last element of its last row
+            else:
+                for r in (0, 1, 2, 3, 4, shape[0] // 2, shape[0] - 1):  # consecutive rows of one column, then far ones
+                    flat[r * row + base] = top if r % 2 == 0 else -top
+    sK = rng.uniform(5e-3, 2e-2, size=s_shape).astype(np.float32)
+    b = np.array([0.3, -0.3, 0.3, 0.1], np.float32)
+    sb = np.array([0.01], np.float32)
+    layers = [(K, sK, b, sb)]
+    Ps, ss = [dev(K), dev(b)], [dev(sK), dev(sb)]
+    out, ws = ops.penalty_fwd(_lib.LQ_PEN_MAXBIN, Ps, ss)
+    assert rel_err(host(out), o.maxbin_penalty(layers)) < TOL
+    dXs, dss = ops.penalty_bwd(_lib.LQ_PEN_MAXBIN, Ps, ss, ws, 1.0)
+    (gK, gsK, gb, gsb), = o.maxbin_penalty_grads(layers, 1.0, accum="fp64")
+    for got, want in ((dXs[0], gK), (dXs[1], gb), (dss[0], gsK), (dss[1], gsb)):
+        got = host(got).astype(np.float64).reshape(want.shape)
+        assert np.array_equal(got != 0, want != 0)                 # exactly the tied elements carry gradient
+        assert float(np.max(np.abs(got - want))) <= TOL * max(float(np.max(np.abs(want))), 1e-30)
+
+
 def test_penalties_many_tensors_and_a_huge_group(lq):
     """More tensors than one kernel-parameter table holds (the scalar stage chains over launches) and a
     per-tensor scale on a 9.4 M-element kernel (more than 4096 partials: the two-level fold)."""
