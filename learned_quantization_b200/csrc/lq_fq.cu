@@ -167,6 +167,13 @@ static BwdThresholdOp<EXT> make_bwd_op(const QMode& qm, float lam) {
   // path), and |dy| >= 0 fails only for a NaN dy.  Only a TINY non-zero lam could underflow the product.
   op.lam_fast = (lam == 0.0f || (lam >= 8.673617379884035e-19f /*2^-60*/ && lam <= 1.152921504606847e+18f /*2^60*/)) ? 1 : 0;
   op.lam_small = (lam > 0.0f && lam < 0.6f) ? 1 : 0;
+  // The filter's proof needs nz = q*s to be eps or of ordinary magnitude (tests/test_oracle_properties.py).  With
+  // floor / rint alone |q*s| <= |P| + |s|; a finite clamp bound of huge magnitude could lift a code far above
+  // P/s (qmin = 1e30) and overflow q*s: such configurations take the exact division for every element.
+  if (EXT) {
+    const float big = 1099511627776.0f;   // 2^40
+    if ((isfinite(qm.qmin) && fabsf(qm.qmin) > big) || (isfinite(qm.qmax) && fabsf(qm.qmax) > big)) op.lam_fast = 0;
+  }
   return op;
 }
 
