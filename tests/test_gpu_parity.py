@@ -444,6 +444,22 @@ def test_rne_clamp_extension(lq):
     assert bits_equal(host(y), y_ref)
     assert np.array_equal(host(codes), q_ref.astype(np.int8))
     assert host(codes).min() == -8 and host(codes).max() == 7
+    # the extension's backward: ordinary clamp bounds (filtered path), and a clamp that lifts every code to 1e30 so
+    # that q*s overflows for the large scales below (exact path; inf / inf ratios poison those groups in the oracle too)
+    dy = rng.normal(0, 1e-3, size=P.shape).astype(np.float32)
+    dy.reshape(-1)[::97] = np.inf
+    s_big = s.copy()
+    s_big[0, ::2, 0] = 1e12
+    for sc, lo, hi in ((s, -8.0, 7.0), (s, -3e38, 3e38), (s_big, 1e30, float("inf"))):
+        with np.errstate(all="ignore"):
+            q_ref, y_ref = o.fq_forward(P, sc, round_mode=o.ROUND_RNE, qmin=lo, qmax=hi)
+            _, ds_ref = o.nested_backward(dy, q_ref, y_ref, sc, 1e-3, accum="fp64")
+        _, ds = ops.fq_bwd_threshold(dev(dy), dev(P), dev(sc), 1e-3, round_mode=_lib.LQ_ROUND_RNE, qmin=lo, qmax=hi)
+        got, want = host(ds).reshape(-1), ds_ref.reshape(-1)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), (lo, hi)
+        assert np.array_equal(np.isinf(got), np.isinf(want)), (lo, hi)
+        ok = np.isfinite(want)
+        assert ds_close(got[ok], want[ok]), (lo, hi)
 
 
 def test_int8_codes_wrap_like_reference_export(lq):
