@@ -231,6 +231,37 @@ int lq_fq_bwd_threshold_finish_p2p(lq_p2p_t* p, const double* local_stats, int64
 int lq_p2p_error(lq_p2p_t* p, int* out_flag);
 int lq_p2p_destroy(lq_p2p_t* p);
 
+/* The data-parallel gradient exchange FUSED with the threshold backward, over NVLink peer memory
+ * (exact mode of SURVEY 8e: all-reduce dy, then NQ:62-118 on the averaged dy on every rank).
+ * lq_dpx_create allocates this rank's arena (cudaMalloc, IPC-exportable; *out_arena is the user part,
+ * arena_bytes long, 256-byte aligned, zero-filled) and returns its 64-byte cudaIpcMemHandle; the host
+ * program gathers the handles of all ranks (world * 64 bytes, rank order) and passes them to
+ * lq_dpx_connect.  The caller lays its flat gradient bucket and the partial workspace out INSIDE the
+ * arena, identically on every rank.
+ * lq_dpx_exchange: ONE persistent kernel per rank.  The work items of the multi-tensor backward over
+ * `descs` (plus the flat range plain[0, n_plain) of unquantised gradients) are dealt round-robin to the
+ * ranks; the owner of an item loads dy from every rank's arena, averages in rank order, applies the
+ * threshold-backward operator with its local P and s, and stores the averaged dy (in place: desc.dX must
+ * be NULL or dy) and the item's partial to every rank.  The ordinary second stage then produces ds,
+ * bit-identical on all ranks.  scale_grad_mode LQ_SGRAD_NONE: everything is only averaged, ds = 0.
+ * desc.dy, plain and ws (>= lq_workspace_bytes(descs, n, LQ_PHASE_BWD)) must lie in the arena; P, s, ds are
+ * ordinary device pointers.  Reference rounding only (floor, no clamp).  Every rank must issue the same
+ * sequence of calls; barrier epochs live on the device, so a call may be captured in a CUDA graph and
+ * replayed.  lq_dpx_error reports (and synchronises for) the time-out flag a rank raises when a peer
+ * does not show up within ~2 s. */
+typedef struct lq_dpx lq_dpx_t;
+int lq_dpx_create(int rank, int world, size_t arena_bytes, lq_dpx_t** out, void* out_handle64, void** out_arena);
+int lq_dpx_connect(lq_dpx_t* x, const void* handles64_all);
+/* same-process peers instead of IPC handles: arenas[r] = the *out_arena of rank r's lq_dpx_create in THIS
+ * process (one process driving several devices with peer access enabled, or -- for tests -- several arenas
+ * on one device, launched on different streams with few enough blocks to be resident together) */
+int lq_dpx_connect_ptrs(lq_dpx_t* x, const void* const* arenas);
+int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, float* plain, int64_t n_plain,
+                    float penalty_threshold, int scale_grad_mode,
+                    void* ws, size_t ws_bytes, lq_stream_t stream);
+int lq_dpx_error(lq_dpx_t* x, int* out_flag);
+int lq_dpx_destroy(lq_dpx_t* x);
+
 #ifdef __cplusplus
 }
 #endif

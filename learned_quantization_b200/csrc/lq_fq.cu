@@ -1,7 +1,7 @@
 // lq_fq.cu -- fake-quant forward (K1), threshold backward (K2), second-stage reduce (K4)
 // and their multi-tensor forms (K5).  Reference semantics: NQ:49-120 (see include/lq.h).
 #include <math.h>
-#include "lq_traverse.cuh"
+#include "lq_fq_ops.cuh"
 #include "lq_col_tma.cuh"
 
 namespace lq {
@@ -33,149 +33,6 @@ struct FwdOp : OpBase<FwdOp<EXT>> {
     y.x = __fmul_rn(q.x, c.s); y.y = __fmul_rn(q.y, c.s); y.z = __fmul_rn(q.z, c.s); y.w = __fmul_rn(q.w, c.s);
   }
 };
-
-// tanhf's own small-argument branch (|x| < 0.6: x + x * x^2 * poly(x^2)), spelled out so that
-// launches with 0 < lambda < 0.6 -- where every evaluated argument lies in (0, lambda] -- skip
-// the exp/rcp branch and its selects.  Same coefficients as libdevice => same values.
-__device__ __forceinline__ float tanh_small(float x) {
-  const float x2 = __fmul_rn(x, x);
-  float t = __fmaf_rn(x2, __uint_as_float(0x3c80f082u) /* 1.5737e-2 */, -5.2303962409496307373e-2f);
-  t = __fmaf_rn(x2, t, 1.331529766321182251e-1f);
-  t = __fmaf_rn(x2, t, -3.3332768082618713379e-1f);
-  t = __fmaf_rn(x2, t, 0.0f);
-  return __fmaf_rn(x, t, x);
-}
-
-// K2  NQ:62-118.  Per element (q, y recomputed in registers instead of re-read from HBM):
-//   nz = (y == 0) ? eps : y                                   NQ:63
-//   r  = |dy| / |nz|                                          NQ:64
-//   max|q|                                                    NQ:68 / NQ:94
-//   below = !(r >= lambda)  (NaN counts as below, like tf.where on r >= lambda)   NQ:97,107
-//   sum  += -|tanh(lambda - r)| for below elements            NQ:109
-// acc.a = sum, acc.b = n_below, acc.c = max|q|.  The group-wide AND of NQ:97 is n_below == 0,
-// resolved in the second stage, which is what lets this be a single pass.
-//
-// Instruction diet (the first version issued 58 instructions per element and sat at 71 % SM
-// issue utilisation next to 81 % of HBM peak):
-//  * P / s through the hoisted reciprocal (div_fast);
-//  * the second IEEE division is only needed where r >= lambda might be false.  With
-//    b = |nz| and lam_hi >= lambda * (1 + 2^-21):   |dy| >= RN(b * lam_hi)  implies
-//    |dy| / b > lambda in the reals (RN loses at most 2^-24 relative; b * lam_hi is a normal
-//    number because b >= min(eps, |s|) >= 2^-40 and lambda >= 2^-60), hence
-//    RN(|dy| / b) >= lambda because rounding is monotone and lambda is representable.
-//    Elements that pass this one-multiply test are "above" and contribute nothing to the
-//    sum or the count; all others (including every NaN) take the exact division;
-//  * tanh_small for 0 < lambda < 0.6;
-//  * the elements that do need the exact division + tanh are rare (3 % at the bench's lambda)
-//    but scattered, so executing them in place ran ~62 % of all warp-instructions of that
-//    branch with 1-2 live lanes (ncu: 20 of 32 threads active per instruction on average).
-//    In the 128-bit ROW path they are pushed to a thread-private shared-memory queue instead
-//    (|dy|, |nz| pairs) and drained once per 16 elements: the branch then runs max_lane(count)
-//    times per 16 elements instead of up to 16 times.
-// Units whose scale or lambda fall outside the windows run the plain formulation.
-template <bool EXT>
-struct BwdThresholdOp : OpBase<BwdThresholdOp<EXT>> {
-  QMode qm;
-  float lam;
-  float lam_hi;      // >= lam * (1 + 2^-21), host-computed
-  int lam_fast;      // lam in [2^-60, 2^60]
-  int lam_small;     // 0 < lam < 0.6
-  using Ctx = Recip;
-  static constexpr int kDeferSlots = 16;
-  static constexpr bool kIn2 = true, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
-  __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
-  __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; x.b += y.b; x.c = fmaxf(x.c, y.c); }
-  // the count and the maximum (non-negative, never NaN: its bit pattern orders like the value) reduce
-  // with one REDUX each; only the float sum needs the shuffle tree
-  __device__ __forceinline__ Acc warp_reduce(const Acc& x) const {
-    Acc r;
-    r.a = warp_sum(x.a);
-    r.b = __reduce_add_sync(0xffffffffu, x.b);
-    r.c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x.c)));
-    return r;
-  }
-  __device__ __forceinline__ Recip prep(float s, const float4&, const Job&) const {
-    Recip r = make_recip(s);
-    r.fast = r.fast && lam_fast;
-    return r;
-  }
-  __device__ __forceinline__ void below(float r, Acc& acc) const {
-    if (!(r >= lam)) {
-      acc.b += 1u;
-      const float x = __fsub_rn(lam, r);
-      acc.a -= fabsf(lam_small ? tanh_small(x) : tanhf(x));
-    }
-  }
-  // plain formulation, any operands
-  __device__ __forceinline__ void slow(float p, float dy, float s, Acc& acc) const {
-    const float q = round_code<EXT>(__fdiv_rn(p, s), qm);
-    const float y = __fmul_rn(q, s);
-    const float nz = (y == 0.0f) ? kEps : y;
-    acc.c = fmaxf(acc.c, fabsf(q));
-    below(__fdiv_rn(fabsf(dy), fabsf(nz)), acc);
-  }
-  // c.fast && fast_range(p) hold
-  __device__ __forceinline__ void fast(float p, float dy, const Recip& c, Acc& acc) const {
-    const float q = round_code<EXT>(div_fast(p, c), qm);
-    const float y = __fmul_rn(q, c.s);
-    const float b = fabsf((y == 0.0f) ? kEps : y);
-    const float a = fabsf(dy);
-    acc.c = fmaxf(acc.c, fabsf(q));
-    if (!(a >= __fmul_rn(b, lam_hi))) below(__fdiv_rn(a, b), acc);
-  }
-  __device__ __forceinline__ void elem(float p, float dy, const Recip& c, const Job&, Acc& acc, float& dx, float&) const {
-    if (c.fast && fast_range(p)) fast(p, dy, c, acc); else slow(p, dy, c.s, acc);
-    dx = dy;   // NQ:118: dP is dy itself
-  }
-  // as fast(), but the maybe-below case is queued instead of executed in place
-  __device__ __forceinline__ void fast_defer(float p, float dy, const Recip& c, Acc& acc, Defer& df) const {
-    const float q = round_code<EXT>(div_fast(p, c), qm);
-    const float y = __fmul_rn(q, c.s);
-    const float nz = (y == 0.0f) ? kEps : y;
-    acc.c = fmaxf(acc.c, fabsf(q));
-    if (!(fabsf(dy) >= __fmul_rn(fabsf(nz), lam_hi))) { df.slot[df.n * 32] = make_float2(dy, nz); ++df.n; }
-  }
-  __device__ __forceinline__ void flush(Acc& acc, Defer& df) const {
-    const int m = __reduce_max_sync(0xffffffffu, df.n);
-    for (int k = 0; k < m; ++k) {
-      if (k < df.n) {
-        const float2 e = df.slot[k * 32];
-        below(__fdiv_rn(fabsf(e.x), fabsf(e.y)), acc);
-      }
-    }
-    df.n = 0;
-  }
-  __device__ __forceinline__ void quad(const float4& p, const float4& d, const Recip& c, const Job&, Acc& acc,
-                                       float4& dx, float4&, Defer& df) const {
-    if (c.fast && fast_range4(p)) {
-      fast_defer(p.x, d.x, c, acc, df); fast_defer(p.y, d.y, c, acc, df);
-      fast_defer(p.z, d.z, c, acc, df); fast_defer(p.w, d.w, c, acc, df);
-    } else {
-      slow(p.x, d.x, c.s, acc); slow(p.y, d.y, c.s, acc); slow(p.z, d.z, c.s, acc); slow(p.w, d.w, c.s, acc);
-    }
-    dx = d;
-  }
-};
-
-template <bool EXT>
-static BwdThresholdOp<EXT> make_bwd_op(const QMode& qm, float lam) {
-  BwdThresholdOp<EXT> op;
-  op.qm = qm; op.lam = lam;
-  op.lam_hi = (float)((double)lam * (1.0 + 1.0 / 1048576.0));     // >= lam*(1+2^-21) after the fp32 rounding
-  // lam == 0 (a reference operating point: every finite ratio is "above") is safe too: lam_hi is then 0,
-  // |nz| * 0 is 0 for every finite nz (NaN for an infinite or NaN one, which sends the element to the exact
-  // path), and |dy| >= 0 fails only for a NaN dy.  Only a TINY non-zero lam could underflow the product.
-  op.lam_fast = (lam == 0.0f || (lam >= 8.673617379884035e-19f /*2^-60*/ && lam <= 1.152921504606847e+18f /*2^60*/)) ? 1 : 0;
-  op.lam_small = (lam > 0.0f && lam < 0.6f) ? 1 : 0;
-  // The filter's proof needs nz = q*s to be eps or of ordinary magnitude (tests/test_oracle_properties.py).  With
-  // floor / rint alone |q*s| <= |P| + |s|; a finite clamp bound of huge magnitude could lift a code far above
-  // P/s (qmin = 1e30) and overflow q*s: such configurations take the exact division for every element.
-  if (EXT) {
-    const float big = 1099511627776.0f;   // 2^40
-    if ((isfinite(qm.qmin) && fabsf(qm.qmin) > big) || (isfinite(qm.qmax) && fabsf(qm.qmax) > big)) op.lam_fast = 0;
-  }
-  return op;
-}
 
 // ------------------------------------------------------------------ K4 second stage
 // One block per group.  Walks the group's partials in index order with a fixed
@@ -360,7 +217,7 @@ Job make_job(const Geom& g, const float* P, const float* s, const float* dy, flo
   return j;
 }
 
-static FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, float lam) {
+FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, float lam) {
   FinJob f{};
   f.part = part; f.ds = ds; f.s = s;
   f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
@@ -433,6 +290,52 @@ int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float
   if (K > 256)
     return launch_after(finalize_warp_kernel<8>, dim3((unsigned)g.C), dim3(256), st, "finalize launch", f);
   return launch_after(finalize_warp_kernel<1>, dim3((unsigned)((g.C + 7) / 8)), dim3(256), st, "finalize launch", f);
+}
+
+// Second stage of a multi-tensor backward: one block per group over all tensors of `fin`.  Groups with more
+// than kFinSplit first-level partials (a per-tensor scale on a large tensor) get the intermediate fold first,
+// exactly as in the single-tensor path, so that no block ever walks more than kFinSplit partials.
+int mt_finalize_launch(FinTable& fin, unsigned groups, cudaStream_t st) {
+  if (fin.n == 0 || groups == 0) return LQ_OK;
+  for (int i = 0; i < fin.n; ++i) {
+    FinJob& f = fin.job[i];
+    if (f.nlin <= 0 || f.regime == REG_LIN) continue;
+    if (f.C * f.nlin > 0x7fffffffll) { set_error("too many intermediate partials"); return LQ_E_BADSHAPE; }
+    int rc = launch_after(fold_partials_kernel, dim3((unsigned)(f.C * f.nlin)), dim3(256), st, "mt fold launch", f);
+    if (rc) return rc;
+    f.part = f.lin; f.regime = REG_LIN;
+  }
+  return launch_after(mt_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "mt finalize launch", fin);
+}
+
+// CL:61-62 / PI:62-64 for a whole table in ONE launch: ds = 0 for every tensor and, where a separate dX was
+// asked for, dX = dy.  Block -> tensor by binary search like the element kernels.
+struct SteJob { const float* dy; float* dX; float* ds; long long n, C; unsigned block_begin; };
+struct SteTable { int n; SteJob job[kMaxMT]; };
+constexpr long long kSteBlockElems = 256 * 4 * 8;   // elements one block copies
+
+__global__ void __launch_bounds__(256) mt_ste_kernel(const __grid_constant__ SteTable tab) {
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const SteJob& j = tab.job[lo];
+  const long long blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
+  const long long e0 = blk * kSteBlockElems;
+  for (long long g = e0 + threadIdx.x; g < j.C && g < e0 + kSteBlockElems; g += 256) j.ds[g] = 0.0f;
+  if (j.dX == nullptr) return;
+  const long long e1 = (e0 + kSteBlockElems < j.n) ? e0 + kSteBlockElems : j.n;
+  if (aligned16_dev(j.dy) && aligned16_dev(j.dX)) {
+    const float4* s4 = reinterpret_cast<const float4*>(j.dy + e0);
+    float4* d4 = reinterpret_cast<float4*>(j.dX + e0);
+    const long long nv = (e1 - e0) >> 2;
+    for (long long v = threadIdx.x; v < nv; v += 256) d4[v] = s4[v];
+    for (long long e = e0 + (nv << 2) + threadIdx.x; e < e1; e += 256) j.dX[e] = j.dy[e];
+  } else {
+    for (long long e = e0 + threadIdx.x; e < e1; e += 256) j.dX[e] = j.dy[e];
+  }
 }
 
 int check_blocks(const Geom& g) {
@@ -574,14 +477,28 @@ extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_th
   QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (scale_grad_mode == LQ_SGRAD_NONE) {     // CL:61-62 / PI:62-64 for every tensor
-    for (int i = 0; i < n; ++i) {
-      const lq_tensor_desc& d = descs[i];
-      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
-      if ((rc = lq_fq_bwd_ste(d.dy, d.dX, d.ds, d.outer * d.C * d.inner, d.C, stream))) return rc;
+  if (scale_grad_mode == LQ_SGRAD_NONE) {     // CL:61-62 / PI:62-64 for every tensor: one launch per 48 tensors
+    for (int i0 = 0; i0 < n; i0 += kMaxMT) {
+      SteTable tab{};
+      unsigned total = 0;
+      for (int i = i0; i < n && i < i0 + kMaxMT; ++i) {
+        const lq_tensor_desc& d = descs[i];
+        if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
+        const long long cnt = d.outer * d.C * d.inner;
+        const bool copy = d.dX != nullptr && d.dX != d.dy && cnt > 0;
+        if (copy && !d.dy) { set_error("lq_mt_fq_bwd: desc %d has null dy", i); return LQ_E_NULLPTR; }
+        if (!copy && !(d.ds && d.C > 0)) continue;
+        const long long work = copy ? (cnt > d.C ? cnt : d.C) : d.C;
+        const long long nb = cdiv(work, kSteBlockElems);
+        if (nb + total > 0x7fffffffll) { set_error("lq_mt_fq_bwd: too many blocks"); return LQ_E_BADSHAPE; }
+        tab.job[tab.n++] = SteJob{d.dy, copy ? d.dX : nullptr, d.ds, cnt, d.ds ? d.C : 0, total};
+        total += (unsigned)nb;
+      }
+      if (total && (rc = launch_after(mt_ste_kernel, dim3(total), dim3(256), st, "mt STE launch", tab))) return rc;
     }
     return LQ_OK;
   }
+  if (ws && !aligned16(ws)) { set_error("lq_mt_fq_bwd: workspace must be 16-byte aligned"); return LQ_E_WORKSPACE; }
   size_t off = 0;
   for (int i0 = 0; i0 < n; i0 += kMaxMT) {
     JobTable tab{};
@@ -613,7 +530,7 @@ extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_th
     if (qm.ext) rc = launch_mt(tab, make_bwd_op<true>(qm, penalty_threshold), st);
     else rc = launch_mt(tab, make_bwd_op<false>(qm, penalty_threshold), st);
     if (rc) return rc;
-    if ((rc = launch_after(mt_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "mt finalize launch", fin))) return rc;
+    if ((rc = mt_finalize_launch(fin, groups, st))) return rc;
   }
   return LQ_OK;
 }

@@ -171,7 +171,9 @@ extern "C" int lq_fq_bwd_threshold_finish_p2p(lq_p2p_t* p, const double* local_s
 extern "C" int lq_p2p_error(lq_p2p_t* p, int* out_flag) {
   if (!p || !out_flag) { set_error("lq_p2p_error: null argument"); return LQ_E_NULLPTR; }
   const int* err = reinterpret_cast<const int*>(static_cast<char*>(p->buf) + p->slots_bytes + p->flags_bytes);
-  return cuda_fail(cudaMemcpy(out_flag, err, sizeof(int), cudaMemcpyDeviceToHost), "lq_p2p_error: cudaMemcpy");   // synchronises
+  int rc = cuda_fail(cudaDeviceSynchronize(), "lq_p2p_error: cudaDeviceSynchronize");   // non-blocking streams included
+  if (rc) return rc;
+  return cuda_fail(cudaMemcpy(out_flag, err, sizeof(int), cudaMemcpyDeviceToHost), "lq_p2p_error: cudaMemcpy");
 }
 
 extern "C" int lq_p2p_destroy(lq_p2p_t* p) {

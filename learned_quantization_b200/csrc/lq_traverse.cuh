@@ -82,9 +82,22 @@ __device__ __forceinline__ void store_code(void* codes, int dtype, long long idx
   else reinterpret_cast<signed char*>(codes)[idx] = (signed char)(int)q;  // wraps like .astype(int8)
 }
 
+// ------------------------------------------------------------------------- where dy / dX / partials live
+// The traversals read the second input (dy), write the output and the unit's partial through an IO policy.
+// LocalIO: this device's memory (every single-device kernel).  lq_dpx.cu supplies PeerIO: dy is the mean over
+// the same address in every rank's peer-mapped arena, outputs and partials are stored to every rank.
+template <bool STREAM>
+struct LocalIO {
+  __device__ __forceinline__ float4 ld_in2_4(const float4* p) const { return ld4<STREAM>(p); }
+  __device__ __forceinline__ float ld_in2_1(const float* p) const { return ld1<STREAM>(p); }
+  __device__ __forceinline__ void st_out4(float4* p, const float4& v) const { st4<STREAM>(p, v); }
+  __device__ __forceinline__ void st_out1(float* p, float v) const { st1<STREAM>(p, v); }
+  __device__ __forceinline__ void st_part(float4* p, const float4& v) const { *p = v; }
+};
+
 // ------------------------------------------------------------------------- ROW regime
-template <class Op, bool STREAM, bool VEC>
-__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op, float2* queue) {
+template <class Op, bool STREAM, bool VEC, class IO = LocalIO<STREAM>>
+__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op, float2* queue, const IO& io = IO()) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
   if (unit >= j.units) return;
@@ -125,7 +138,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         const int v = v0 + u * 32 + lane;
         if (v < nvec) {
           p[u] = ld4<STREAM>(P4 + v);
-          if (Op::kIn2) d[u] = ld4<STREAM>(D4 + v);
+          if (Op::kIn2) d[u] = io.ld_in2_4(D4 + v);
         }
       }
 #pragma unroll
@@ -134,7 +147,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         if (v < nvec) {
           float4 o, c;
           op.quad(p[u], Op::kIn2 ? d[u] : make_float4(0.f, 0.f, 0.f, 0.f), ctx, j, acc, o, c, df);
-          if (wr) st4<STREAM>(O4 + v, o);
+          if (wr) io.st_out4(O4 + v, o);
           if (Op::kCodes && j.codes) {
             const long long e = base + 4ll * v;
             store_code(j.codes, j.codes_dtype, e + 0, c.x);
@@ -154,7 +167,7 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         const int e = e0 + u * 32 + lane;
         if (e < len) {
           p[u] = ld1<STREAM>(j.P + base + e);
-          if (Op::kIn2) d[u] = ld1<STREAM>(j.dy + base + e);
+          if (Op::kIn2) d[u] = io.ld_in2_1(j.dy + base + e);
         }
       }
 #pragma unroll
@@ -163,15 +176,15 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
         if (e < len) {
           float o, c;
           op.elem(p[u], Op::kIn2 ? d[u] : 0.f, ctx, j, acc, o, c);
-          if (wr) st1<STREAM>(out + base + e, o);
+          if (wr) io.st_out1(out + base + e, o);
           if (Op::kCodes && j.codes) store_code(j.codes, j.codes_dtype, base + e, c);
         }
       }
     }
   }
-  if (Op::kReduce) {
+  if (Op::kReduce && j.part != nullptr) {
     acc = op.warp_reduce(acc);
-    if (lane == 0) j.part[unit] = pack_acc(acc);
+    if (lane == 0) io.st_part(j.part + unit, pack_acc(acc));
   }
 }
 
@@ -183,8 +196,8 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
 // thread.  This is the path of every two-input reducing operator (the threshold backward): with
 // four columns per thread their per-thread state for four groups cost 50 % more instructions and
 // ran at 4.2 TB/s where ROW reaches 6.3.
-template <class Op, bool STREAM>
-__device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue) {
+template <class Op, bool STREAM, class IO = LocalIO<STREAM>>
+__device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue, const IO& io = IO()) {
   constexpr int U = 8;
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
@@ -221,7 +234,7 @@ __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& o
     for (int u = 0; u < U; ++u) {
       if (i0 + u < rows_mine) {
         p[u] = ld1<STREAM>(Pp + u * stride);
-        if (Op::kIn2) d[u] = ld1<STREAM>(Dp + u * stride);
+        if (Op::kIn2) d[u] = io.ld_in2_1(Dp + u * stride);
       }
     }
 #pragma unroll
@@ -233,8 +246,8 @@ __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& o
                 Op::kIn2 ? make_float4(d[4 * qd], d[4 * qd + 1], d[4 * qd + 2], d[4 * qd + 3]) : make_float4(0.f, 0.f, 0.f, 0.f),
                 ctx, j, acc, o, c, df);
         if (wr) {
-          st1<STREAM>(Op_ + (4 * qd) * stride, o.x); st1<STREAM>(Op_ + (4 * qd + 1) * stride, o.y);
-          st1<STREAM>(Op_ + (4 * qd + 2) * stride, o.z); st1<STREAM>(Op_ + (4 * qd + 3) * stride, o.w);
+          io.st_out1(Op_ + (4 * qd) * stride, o.x); io.st_out1(Op_ + (4 * qd + 1) * stride, o.y);
+          io.st_out1(Op_ + (4 * qd + 2) * stride, o.z); io.st_out1(Op_ + (4 * qd + 3) * stride, o.w);
         }
         if (Op::kCodes && j.codes) {
           const long long e = base + (long long)i * stride;
@@ -247,7 +260,7 @@ __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& o
           if (i + v < rows_mine) {
             float o, c;
             op.elem(p[4 * qd + v], Op::kIn2 ? d[4 * qd + v] : 0.f, ctx, j, acc, o, c);
-            if (wr) st1<STREAM>(Op_ + (4 * qd + v) * stride, o);
+            if (wr) io.st_out1(Op_ + (4 * qd + v) * stride, o);
             if (Op::kCodes && j.codes) store_code(j.codes, j.codes_dtype, base + (long long)(i + v) * stride, c);
           }
         }
@@ -275,7 +288,7 @@ __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& o
       __syncthreads();
       acc = smem[t];
     }
-    if (ty == 0 && col < j.ncol) j.part[chunk * j.W + col] = pack_acc(acc);
+    if (ty == 0 && col < j.ncol) io.st_part(j.part + chunk * j.W + col, pack_acc(acc));
   }
 }
 
@@ -504,6 +517,8 @@ int fq_bwd_elements_launch(const Geom& g, const float* dy, const float* P, const
                            float* dX, float4* part, const QMode& qm, cudaStream_t st);
 int fq_finalize_launch(const Geom& g, const float4* part, float* ds, const float* s, float lam, cudaStream_t st, int mode = 0);
 int check_blocks(const Geom& g);
+FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, float lam);
+int mt_finalize_launch(FinTable& fin, unsigned groups, cudaStream_t st);
 Job make_job(const Geom& g, const float* P, const float* s, const float* dy, float* y, float* dX,
              void* codes, int codes_dtype, float4* part);
 

@@ -141,6 +141,87 @@ class P2PFinish:
             self._h = C.c_void_p()
 
 
+class _DeviceSpan:
+    """__cuda_array_interface__ over a raw device allocation owned by `owner` (kept alive by the tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerComm(Comm):
+    """lq_dpx_* (include/lq.h): the gradient exchange fused with the threshold backward in ONE kernel over
+    NVLink peer memory.  The flat gradient bucket and the partial workspace live in an IPC arena that every
+    peer maps; allocate() creates it (collective: every rank must call it with the same size) and returns
+    it as a uint8 CUDA tensor.  No NCCL call is involved, so a step that uses it is captured as one CUDA graph."""
+
+    def __init__(self, rank: Optional[int] = None, world: Optional[int] = None):
+        import torch.distributed as dist
+        if rank is None:
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        self.rank, self.world = int(rank), int(world)
+        self._h = C.c_void_p()
+        self.arena: Optional[torch.Tensor] = None
+
+    def allocate(self, nbytes: int) -> torch.Tensor:
+        import torch.distributed as dist
+        if self._h:
+            raise RuntimeError("PeerComm.allocate may be called once")
+        mine = C.create_string_buffer(64)
+        base = C.c_void_p()
+        err = None
+        try:
+            check(lib.lq_dpx_create(self.rank, self.world, int(nbytes), C.byref(self._h), mine, C.byref(base)))
+        except _lib.LqError as e:
+            err = str(e)
+        if self.world > 1:          # every rank reaches every collective: a local failure raises everywhere
+            got = [None] * self.world
+            dist.all_gather_object(got, (err, bytes(mine.raw)))
+            errs = [e for e, _ in got if e]
+            if not errs:
+                try:
+                    check(lib.lq_dpx_connect(self._h, b"".join(h for _, h in got)))
+                except _lib.LqError as e:
+                    err = str(e)
+                got2 = [None] * self.world
+                dist.all_gather_object(got2, err)
+                errs = [e for e in got2 if e]
+            if errs:
+                self.close()
+                raise _lib.LqError(_lib.LQ_E_CUDA, "peer-memory exchange unavailable: " + errs[0])
+        elif err:
+            raise _lib.LqError(_lib.LQ_E_CUDA, err)
+        nbytes = -(-int(nbytes) // 256) * 256
+        self.arena = torch.as_tensor(_DeviceSpan(base.value, nbytes, self), device=torch.device("cuda", torch.cuda.current_device()))
+        return self.arena
+
+    def exchange(self, descs, n: int, plain: Optional[torch.Tensor], penalty_threshold: float, scale_grad_mode: int,
+                 ws: Optional[torch.Tensor]) -> None:
+        """mean-allreduce of every desc.dy and of `plain` (in place) + the scale gradients of the averaged dy."""
+        check(lib.lq_dpx_exchange(self._h, descs, n,
+                                  None if plain is None or plain.numel() == 0 else plain.data_ptr(),
+                                  0 if plain is None else plain.numel(), float(penalty_threshold), int(scale_grad_mode),
+                                  None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(),
+                                  torch.cuda.current_stream().cuda_stream))
+
+    def allreduce_mean_(self, flat: torch.Tensor) -> None:
+        """Plain in-place mean all-reduce of a slice of the arena."""
+        if flat.numel():
+            self.exchange(None, 0, flat, 0.0, _lib.LQ_SGRAD_NONE, None)
+
+    def timed_out(self) -> bool:
+        flag = C.c_int(0)
+        check(lib.lq_dpx_error(self._h, C.byref(flag)))
+        return bool(flag.value)
+
+    def close(self):
+        if self._h:
+            self.arena = None
+            check(lib.lq_dpx_destroy(self._h))
+            self._h = C.c_void_p()
+
+
 class TorchDistComm(Comm):
     """The same interface over a torch.distributed process group (gloo on CPU in the tests)."""
 
@@ -159,7 +240,8 @@ class TorchDistComm(Comm):
 class GradBucket:
     """One flat fp32 buffer with views for every gradient, in the order [dy | plain | ds]."""
 
-    def __init__(self, quant_shapes: Sequence, plain_shapes: Sequence, scale_shapes: Sequence, device, align: int = 4):
+    def __init__(self, quant_shapes: Sequence, plain_shapes: Sequence, scale_shapes: Sequence, device, align: int = 4,
+                 alloc: Optional[Callable[[int], torch.Tensor]] = None):
         """Each entry is a shape, or a tensor whose memory layout the view must reproduce (a kernel stored
         as OHWI keeps that order inside the bucket: copies into it and the optimizer stay flat)."""
         def carve(items, off):
@@ -178,11 +260,15 @@ class GradBucket:
                 off += -(-n // align) * align        # keep every view 16-byte aligned for the 128-bit paths
             return spans, off
         q, off = carve(quant_shapes, 0)
+        self.plain_begin = off
         p, off = carve(plain_shapes, off)
         self.n_exact = off                            # [dy | plain] is what EXACT mode exchanges
         s, off = carve(scale_shapes, off)
         self.n_total = off
-        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        # alloc(n_floats) supplies the storage instead (PeerComm: a slice of the peer-mapped arena)
+        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=device) if alloc is None else alloc(max(off, 1))
+        if self.flat.dtype != torch.float32 or self.flat.numel() < max(off, 1) or not self.flat.is_contiguous():
+            raise ValueError("bucket storage must be a contiguous fp32 tensor of at least n_total elements")
         def view(span):
             off, n, shp, perm = span
             base = self.flat[off:off + n]

@@ -22,7 +22,7 @@ from torch import nn
 
 from .. import _lib, ops
 from ..custom_components import _impl
-from .dp import Comm, GradBucket, SingleComm, exchange_gradients
+from .dp import Comm, GradBucket, PeerComm, SingleComm, exchange_gradients
 
 
 def quantised_pairs(model: nn.Module):
@@ -107,7 +107,26 @@ class TrainStep:
         quant_ids = {id(p) for p in b.params} | {id(s) for s in b.scales}
         self.plain = [p for p in model.parameters() if id(p) not in quant_ids and p.requires_grad]
         dev = b.params[0].device
-        self.bucket = GradBucket(list(b.params), [p.shape for p in self.plain], [s.shape for s in b.scales], dev)
+        self._peer = isinstance(self.comm, PeerComm)
+        self._xws = None
+        alloc = None
+        if self._peer:
+            # the bucket and the partial workspace of the fused exchange live in the peer-mapped arena
+            ws_bytes = ops.workspace_bytes([ops.make_desc(layout=l) for l in b.layouts], _lib.LQ_PHASE_BWD)
+
+            def alloc(n_floats):
+                nb = -(-n_floats * 4 // 256) * 256
+                arena = self.comm.allocate(nb + max(ws_bytes, 256))
+                self._xws = arena[nb:]
+                return arena[:n_floats * 4].view(torch.float32)
+        self.bucket = GradBucket(list(b.params), [p.shape for p in self.plain], [s.shape for s in b.scales], dev,
+                                 alloc=alloc)
+        if self._peer:
+            threshold = b.sgrad_mode == _lib.LQ_SGRAD_THRESHOLD
+            self._xdescs = ops.desc_array([
+                ops.make_desc(P=p.data, s=s.data, dy=dy, ds=(ds if threshold else None), layout=l)
+                for p, s, dy, ds, l in zip(b.params, b.scales, self.bucket.dy, self.bucket.ds, b.layouts)])
+            self._xplain = self.bucket.flat[self.bucket.plain_begin:self.bucket.n_exact]
         # optimizer table over [P | plain | s], gradients = the bucket views (pointers never change)
         l2 = []
         for host in b.hosts:
@@ -168,10 +187,32 @@ class TrainStep:
             else:
                 ops.opt_sgd(self.table, self.lr, self.momentum, self.nesterov)
 
-    def __call__(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
-        loss = self._forward_backward(x, y_true)
+    def _exchange(self, scale_backward=None):
+        """gradient exchange + scale backward, ordered as ds_mode says (training/dp.py)."""
+        scale_backward = scale_backward or self._scale_backward
         with torch.no_grad():
-            exchange_gradients(self.bucket, self.comm, self._scale_backward, self.ds_mode)
+            if not self._peer:
+                exchange_gradients(self.bucket, self.comm, scale_backward, self.ds_mode)
+            elif self.ds_mode == "exact":
+                # ONE kernel: mean of [dy | plain] over the ranks' arenas + the threshold backward of the mean
+                b = self.bank
+                self.comm.exchange(self._xdescs, len(self._xdescs), self._xplain, b.lam, b.sgrad_mode, self._xws)
+                if b.sgrad_mode == _lib.LQ_SGRAD_NONE:
+                    self.bucket.flat[self.bucket.n_exact:self.bucket.n_total].zero_()
+            elif self.ds_mode == "local":
+                scale_backward()
+                self.comm.allreduce_mean_(self.bucket.all())
+            else:
+                raise ValueError(f"mode must be 'exact' or 'local', got {self.ds_mode!r}")
+
+    def __call__(self, x: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:
+        try:
+            loss = self._forward_backward(x, y_true)
+        finally:
+            # the banked y are valid for THIS step's parameters only: a later model(x) (validation, callbacks)
+            # must quantise the updated parameters through the per-layer path
+            self.bank.release()
+        self._exchange()
         self._update()
         self.iterations += 1
         return loss
@@ -194,7 +235,7 @@ class TrainStep:
                 self(self._sx, self._sy)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if self.comm.world == 1:
+        if self.comm.world == 1 or self._peer:      # no library collective inside: the whole step is one graph
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._sloss = self(self._sx, self._sy)
@@ -204,6 +245,7 @@ class TrainStep:
         ga, gs, gu = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga):
             self._sloss = self._forward_backward(self._sx, self._sy)
+        self.bank.release()
         pool = ga.pool()
         with torch.cuda.graph(gs, pool=pool):
             self._scale_backward()
@@ -226,7 +268,7 @@ class TrainStep:
         else:
             ga, gs, gu = self._graph
             ga.replay()
-            exchange_gradients(self.bucket, self.comm, gs.replay, self.ds_mode)
+            self._exchange(gs.replay)
             gu.replay()
         self.iterations += 1
         return self._sloss

@@ -46,7 +46,7 @@ def _data():
     return torch.rand(B, 10, 10, 3, generator=g), torch.randint(0, 10, (B,), generator=g)
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, kind="nccl", graph_steps=0):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -54,19 +54,27 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
         sparse_categorical_crossentropy as scce
-    from learned_quantization_b200.training.dp import NcclComm
+    from learned_quantization_b200.training.dp import NcclComm, PeerComm
     from learned_quantization_b200.training.step import TrainStep
     torch.manual_seed(0)
     x, y = _data()
     x, y = x.cuda(), y.cuda()
     net = _net().cuda()
     _prepare(net, x)
-    comm = NcclComm()
+    comm = NcclComm() if kind == "nccl" else PeerComm()
     step = TrainStep(net, scce, optimizer="adam", lr=LR, comm=comm, ds_mode="exact")
     lo, hi = rank * B // world, (rank + 1) * B // world
-    for _ in range(STEPS):
-        step(x[lo:hi], y[lo:hi])
+    if graph_steps:                 # capture() runs 3 eager steps itself; the rest are replays of ONE graph
+        step.capture(x[lo:hi].contiguous(), y[lo:hi].contiguous(), warmup=3)
+        assert len(step._graph) == (1 if kind == "peer" else 3)
+        for _ in range(graph_steps - 3):
+            step.replay(x[lo:hi], y[lo:hi])
+    else:
+        for _ in range(STEPS):
+            step(x[lo:hi], y[lo:hi])
     torch.cuda.synchronize()
+    if kind == "peer":
+        assert not comm.timed_out()
     params = [p.detach().cpu().numpy().copy() for p in net.parameters()]
     gathered = [None] * world
     dist.all_gather_object(gathered, params)
@@ -78,14 +86,7 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_device_on_the_whole_batch(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    import torch.multiprocessing as mp
-    out = str(tmp_path / "dp.npz")
-    mp.spawn(_worker, args=(2, 29671, out), nprocs=2, join=True)
-    got = np.load(out)
-    # the same two steps on one device with the whole batch
+def _single_device(steps):
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
         sparse_categorical_crossentropy as scce
     from learned_quantization_b200.training.step import TrainStep
@@ -96,8 +97,22 @@ def test_two_ranks_equal_one_device_on_the_whole_batch(tmp_path):
     net = _net().cuda()
     _prepare(net, x)
     step = TrainStep(net, scce, optimizer="adam", lr=LR)
-    for _ in range(STEPS):
+    for _ in range(steps):
         step(x, y)
-    for i, p in enumerate(net.parameters()):
-        want = p.detach().cpu().numpy()
-        assert float(np.max(np.abs(got[f"arr_{i}"] - want))) <= 0.02 * LR, i
+    return [p.detach().cpu().numpy() for p in net.parameters()]
+
+
+@pytest.mark.parametrize("kind,graph_steps", [("nccl", 0), ("peer", 0), ("peer", 5)])
+def test_two_ranks_equal_one_device_on_the_whole_batch(tmp_path, kind, graph_steps):
+    """kind "nccl": lq_dp_allreduce + lq_mt_fq_bwd; "peer": the fused peer-memory exchange (lq_dpx_exchange),
+    eager and as ONE CUDA graph per step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dp.npz")
+    port = 29671 + (0 if kind == "nccl" else 1) + graph_steps
+    mp.spawn(_worker, args=(2, port, out, kind, graph_steps), nprocs=2, join=True)
+    got = np.load(out)
+    steps = graph_steps or STEPS
+    for i, want in enumerate(_single_device(steps)):          # the same steps on one device with the whole batch
+        assert float(np.max(np.abs(got[f"arr_{i}"] - want))) <= 0.02 * LR * steps / STEPS, i
