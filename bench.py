@@ -121,31 +121,35 @@ def cpu_oracle():
     return _CO
 
 
-def cpu_oracle_step(P, s, dy, layout, lam):
-    return cpu_oracle().fwd_bwd(P, s, dy, layout, lam)
+def cpu_oracle_step(P, s, dy, layout, lam, out=None):
+    return cpu_oracle().fwd_bwd(P, s, dy, layout, lam, out)
 
 
 def cpu_sample(sample_outer):
+    import numpy as np
     layout = (sample_outer, LAYOUT[1], LAYOUT[2])
     P, s, dy = synth(layout, 42)
-    return layout, P, s, dy
+    out = (np.empty(P.size, np.float32), np.empty(P.size, np.float32))
+    return layout, P, s, dy, out
 
 
 def cpu_describe(layout, n, dt):
     co = cpu_oracle()
-    return {"unit": UNIT, "cores": co.threads, "kind": "port",
+    whole = layout[0] == LAYOUT[0]
+    return {"unit": UNIT, "cores": co.threads, "kind": "port", "baseline_kind": "c_port", "same_config": whole,
             "sample": f"oracle/lq_oracle.c (reference op chain NQ:55-118, OpenMP x{co.threads}) fwd+bwd on "
-                      f"[{layout[0]},{layout[1]},{layout[2]}] = {n} elements of the workload, {dt * 1e3:.1f} ms per pass",
+                      f"[{layout[0]},{layout[1]},{layout[2]}] = {n} elements "
+                      + ("(the whole workload tensor)" if whole else "of the workload") + f", {dt * 1e3:.1f} ms per pass",
             "host_cpus": os.cpu_count()}
 
 
 def cpu_baseline(sample_outer=32, budget_s=12.0):
-    layout, P, s, dy = cpu_sample(sample_outer)
-    cpu_oracle_step(P, s, dy, layout, LAMBDA)          # warm (page faults, thread pool)
+    layout, P, s, dy, out = cpu_sample(sample_outer)
+    cpu_oracle_step(P, s, dy, layout, LAMBDA, out)          # warm (page faults, thread pool)
     t0 = time.perf_counter()
     reps = 0
     while True:
-        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+        cpu_oracle_step(P, s, dy, layout, LAMBDA, out)
         reps += 1
         if time.perf_counter() - t0 > budget_s or reps >= 200:
             break
@@ -155,33 +159,68 @@ def cpu_baseline(sample_outer=32, budget_s=12.0):
     return cb
 
 
+def mnist_cpu(budget_s=6.0):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: one training step of the MNIST model
+    (Flatten -> CustomDense(128) -> relu -> CustomDense(10) -> softmax, batch 32, Adam 1e-4, per-tensor scales)
+    restated on the oracle (oracle/mnist_step.py), end to end on the host: nested variant and the MaxBin
+    loss-term variant.  images/s; a reported baseline."""
+    import numpy as np
+    from oracle.mnist_step import MnistOracle
+    rng = np.random.default_rng(42)
+    X = (rng.random((32, 784)) * 255).astype(np.float32)     # the reference feeds un-normalised pixels
+    Y = rng.integers(0, 10, 32)
+    out = {"unit": "images/s", "kind": "port", "batch": 32, "cores": 1,
+           "sample": "oracle/mnist_step.py (numpy fp32; fake-quant fwd, nested / loss-term bwd, Keras Adam, "
+                     "MinValueConstraint), steps of batch 32 for ~%.0f s per variant" % (budget_s / 2)}
+    for name, variant, value in (("nested", "nested", 1e-10), ("custom_loss_maxbin", "maxbin", 1e-9)):
+        m = MnistOracle.init(seed=42, orientation="scalar", variant=variant, value=value, lr=1e-4)
+        m.step(X, Y)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget_s / 2:
+            m.step(X, Y)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"value": 32 / dt, "ms_per_step": dt * 1e3, "steps": reps}
+    out["value"] = out["nested"]["value"]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # torchrun pins OMP_NUM_THREADS=1 for its children; this arm is one process and uses every host core
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    sample_outer = 32     # 8 Mi elements per step
-    layout, P, s, dy = cpu_sample(sample_outer)
-    for _ in range(args.warmup):
-        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+    sample_outer = LAYOUT[0]      # the WHOLE 64 Mi-element tensor per step: same config as the GPU arm
+    layout, P, s, dy, out = cpu_sample(sample_outer)
+    cpu_oracle_step(P, s, dy, layout, LAMBDA, out)
+    t1 = time.perf_counter()
+    cpu_oracle_step(P, s, dy, layout, LAMBDA, out)
+    one = time.perf_counter() - t1
+    # bounded: the whole --steps/--warmup run stays within ~2 minutes on any host
+    steps = max(3, min(args.steps, int(90.0 / max(one, 1e-3))))
+    warm = max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        cpu_oracle_step(P, s, dy, layout, LAMBDA, out)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_oracle_step(P, s, dy, layout, LAMBDA)
+    for _ in range(steps):
+        cpu_oracle_step(P, s, dy, layout, LAMBDA, out)
     dt = time.perf_counter() - t0
-    val = (BYTES_FWD + BYTES_BWD) * P.size * args.steps / dt / 1e9
-    cb = cpu_describe(layout, P.size, dt / args.steps)
+    val = (BYTES_FWD + BYTES_BWD) * P.size * steps / dt / 1e9
+    cb = cpu_describe(layout, P.size, dt / steps)
     cb["value"] = val
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "layout": list(LAYOUT),
-                   "lambda": LAMBDA, "step": f"bounded sample [{sample_outer},512,512] of the 64Mi-element tensor",
+                   "lambda": LAMBDA, "step": "the whole 64Mi-element tensor, forward + nested backward",
                    "note": "reference CPU path = TensorFlow-CPU (not installable); timed stand-in is the op-for-op C port"},
-        "elements_per_s": P.size * args.steps / dt,
+        "same_config": True, "baseline_kind": "c_port",
+        "elements_per_s": P.size * steps / dt,
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mnist_cpu": mnist_cpu(),
     }))
 
 
@@ -201,7 +240,7 @@ def run_ours(args):
     import learned_quantization_b200 as lq
     ops = lq.ops
     if args.only_qat:
-        q = run_qat(args, rank, world, local, model=args.qat_model)
+        q = run_qat(args, rank, world, local, args.qat_config)
         if rank == 0:
             print(json.dumps(q))
         if world > 1:
@@ -396,54 +435,171 @@ def run_ours(args):
             p2p.close()
         comm.close()
         comm = None
-    qat = qat_cifar = None
+    extra = {}
     if not args.no_qat:
         del sets, y, dX, hP, hdy, hy, hws
         torch.cuda.empty_cache()
-        qat = run_qat(args, rank, world, local)
-        if world == 1:                     # BASELINE configs[1] is a single-GPU configuration
+        if world > 1:
+            extra["dp_selfcheck"] = dp_selfcheck(args, rank, world)
+            if not extra["dp_selfcheck"].get("ok"):
+                args.qat_comm = "nccl"            # never time an exchange that does not reproduce the single device
+        for key in qat_keys(world):
             try:
-                qat_cifar = run_qat(args, rank, world, local, model="cifar_paper")
-            except Exception as e:         # reported, never allowed to take the headline line down
-                qat_cifar = {"error": f"{type(e).__name__}: {e}"}
+                extra[key] = run_qat(args, rank, world, local, key)
+            except Exception as e:                # reported, never allowed to take the headline line down
+                extra[key] = {"error": f"{type(e).__name__}: {e}"}
+                if world > 1:
+                    raise
+        if world == 1:
+            extra["mnist_cpu"] = mnist_cpu()
     if rank == 0:
-        if qat is not None:
-            line["qat"] = qat
-        if qat_cifar is not None:
-            line["qat_cifar_paper"] = qat_cifar
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------- QAT training step
-def run_qat(args, rank, world, local, model="imagenette"):
-    """Second half of BASELINE.json's metric: QAT images/s on the IMAGENETTE ResNet-style model
-    (20 quantised convs + biases = 40 quantised tensors, nested variant, channelwise scales,
-    lambda 1e-11, Adam 1e-4, 224x224x3, per-GPU batch 64 = the reference's batch), synthetic data.
-    Data parallel: batch sharded, [dy | plain grads] mean-allreduced through lq_dp_allreduce
-    (our NCCL communicator), scale gradients in EXACT mode (training/dp.py).  Weak scaling.
-    model="cifar_paper": BASELINE configs[1] instead -- CIFAR-10/paper_implementation ResNet-18 on
-    CustomConv2DLayerNoBias + quantised fc (22 tensors, STE scale gradient PI:62-64, channelwise scales),
-    32x32x3, batch 256, SGD(0.1, momentum 0.9, nesterov, weight decay 5e-4) (experiment.py:130-141)."""
+# Every training configuration BASELINE.json names, by key of the JSON line:
+QAT_CONFIGS = {
+    # IMAGENETTE nested, the reference's own batch (64 per GPU)
+    "qat": dict(model="imagenette", variant="nested", batch=64),
+    # configs[4]: IMAGENETTE nested at 224x224, batch 1024 sharded over 8 GPUs = 128 per GPU
+    "qat_b128": dict(model="imagenette", variant="nested", batch=128),
+    # configs[2]: IMAGENETTE custom_loss_terms (MaxBin, gamma 1e-9), data parallel
+    "qat_custom_loss": dict(model="imagenette", variant="custom_loss", loss="maxbin", batch=64),
+    # configs[1]: CIFAR-10 paper_implementation ResNet-18, per-channel LEARNED scale (threshold rule), batch 256, 1 GPU
+    "qat_cifar_paper": dict(model="cifar_paper", sgrad="threshold", batch=256),
+    # the same model with the reference's stub backward (PI:62-64: ds = zeros)
+    "qat_cifar_paper_ste": dict(model="cifar_paper", sgrad="none", batch=256),
+    # configs[0] on the GPU (its CPU figure is `mnist_cpu`): MNIST MLP, nested, per-tensor scales, batch 32
+    "qat_mnist": dict(model="mnist", variant="nested", batch=32),
+}
+
+
+def qat_keys(world):
+    if world == 1:
+        return ["qat", "qat_b128", "qat_custom_loss", "qat_cifar_paper", "qat_cifar_paper_ste", "qat_mnist"]
+    return ["qat", "qat_b128", "qat_custom_loss"]          # the data-parallel configurations
+
+
+def make_comm(args, world):
+    from learned_quantization_b200.training.dp import NcclComm, PeerComm
+    if world == 1:
+        return None, "single device"
+    if args.qat_comm == "peer":
+        return PeerComm(), "lq_dpx_exchange: fused peer-memory all-reduce + threshold backward (one kernel, in the step's graph)"
+    return NcclComm(), "lq_dp_allreduce (ncclAllReduce avg) between two graphs + lq_mt_fq_bwd"
+
+
+def dp_selfcheck(args, rank, world):
+    """Before any data-parallel number is timed: two steps of a small quantised model on `world` ranks, each
+    with its shard of a batch, must end where ONE device with the whole batch ends (exact mode), and every
+    rank must hold bit-identical parameters.  (tests/test_gpu_dp.py does the same under pytest, but the
+    round-end test box has a single GPU.)"""
     import torch
     import torch.distributed as dist
+    import learned_quantization_b200 as lq
+    from learned_quantization_b200 import RandomNormal
+    from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
+        sparse_categorical_crossentropy as scce
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.training.step import TrainStep
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            init = RandomNormal(seed=9)
+            self.c1 = nq.CustomConv2DLayer(seed=9, penalty_threshold=1e-3, orientation="channelwise", initializer=init,
+                                           filters=8, kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
+                                           regularizer=None, kernel_storage="ohwi")
+            self.fc = nq.CustomDenseLayer(seed=9, units=10, penalty_threshold=1e-3, orientation="rowwise",
+                                          initializer=init, name="fc", regularizer=None)
+
+        def forward(self, x):
+            return torch.softmax(self.fc(torch.relu(self.c1(x)).mean(dim=(1, 2))), dim=-1)
+
+    B, lr, steps = 2 * world, 1e-3, 2
+    g = torch.Generator().manual_seed(11)
+    x, y = torch.rand(B, 10, 10, 3, generator=g).cuda(), torch.randint(0, 10, (B,), generator=g).cuda()
+
+    def build():
+        torch.manual_seed(0)
+        net = Net().cuda()
+        net(x[:1])
+        gs = torch.Generator(device="cuda").manual_seed(3)
+        with torch.no_grad():
+            for q in (net.c1.nested_q_k_layer, net.c1.nested_q_b_layer, net.fc.nested_q_w_layer, net.fc.nested_q_b_layer):
+                q.scale.copy_(torch.empty_like(q.scale).uniform_(5e-3, 2e-2, generator=gs))
+        return net
+
+    out = {"kind": args.qat_comm, "steps": steps, "global_batch": B}
+    try:
+        comm, _ = make_comm(args, world)
+        net = build()
+        step = TrainStep(net, scce, optimizer="adam", lr=lr, comm=comm, ds_mode="exact")
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        for _ in range(steps):
+            step(x[lo:hi], y[lo:hi])
+        torch.cuda.synchronize()
+        timed_out = bool(getattr(comm, "timed_out", lambda: False)())
+        ref = build()
+        one = TrainStep(ref, scce, optimizer="adam", lr=lr)
+        for _ in range(steps):
+            one(x, y)
+        diff = max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+        flat = torch.cat([p.detach().flatten() for p in net.parameters()]).view(torch.int32)
+        mine = torch.stack([flat.sum(dtype=torch.int64), (flat.to(torch.int64) * torch.arange(1, flat.numel() + 1, device="cuda")).sum()])
+        allsums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+        identical = all(bool(torch.equal(a, allsums[0])) for a in allsums)
+        ok = torch.tensor([1 if (diff <= 0.02 * lr and identical and not timed_out) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        out.update(ok=bool(int(ok)), max_abs_diff_vs_single_device=diff, tolerance=0.02 * lr,
+                   ranks_bit_identical=identical, timed_out=timed_out)
+        comm.close()
+    except lq.LqError as e:                       # raised on every rank together (PeerComm.allocate is collective)
+        out.update(ok=False, error=str(e))
+    return out
+
+
+def run_qat(args, rank, world, local, key="qat"):
+    """Second half of BASELINE.json's metric: QAT images/s of one training configuration (QAT_CONFIGS), synthetic data.
+    imagenette: ResNet-style model (20 quantised convs + biases = 40 quantised tensors, channelwise scales, Adam 1e-4,
+    224x224x3; nested: lambda 1e-11 with the threshold backward, custom_loss: gamma 1e-9 MaxBin with the STE backward).
+    cifar_paper: CIFAR-10/paper_implementation ResNet-18 on CustomConv2DLayerNoBias + quantised fc (22 tensors,
+    channelwise scales), 32x32x3, batch 256, SGD(0.1, momentum 0.9, nesterov, weight decay 5e-4) (experiment.py:130-141).
+    mnist: Flatten -> Dense128 -> relu -> Dense10 -> softmax, per-tensor scales, batch 32, Adam 1e-4.
+    Data parallel: batch sharded, gradients exchanged in EXACT mode (training/dp.py).  Weak scaling."""
+    import torch
+    import torch.distributed as dist
+    import learned_quantization_b200 as lq
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
         sparse_categorical_crossentropy as scce
     from learned_quantization_b200.training import models
-    from learned_quantization_b200.training.dp import NcclComm
     from learned_quantization_b200.training.step import TrainStep
 
+    cfg = dict(QAT_CONFIGS[key])
+    if key == "qat":                                  # the debugging flags act on the default configuration
+        cfg.update(batch=args.qat_batch, variant=args.qat_variant, loss=args.qat_loss)
     torch.backends.cudnn.allow_tf32 = True           # TF 2.11 enables TF32 convolutions by default too
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
-    cifar = model == "cifar_paper"
-    batch, shape = (256, (32, 32, 3)) if cifar else (args.qat_batch, (224, 224, 3))
+    model, batch = cfg["model"], cfg["batch"]
+    cifar, mnist = model == "cifar_paper", model == "mnist"
+    shape = (32, 32, 3) if cifar else ((28, 28, 1) if mnist else (224, 224, 3))
     torch.manual_seed(42)
-    variant = "paper" if cifar else args.qat_variant
-    value = 0.0 if cifar else (1e-11 if variant == "nested" else 1e-9)   # lambda (nested) / gamma (custom loss), chapter4.tex
+    variant = "paper" if cifar else cfg["variant"]
+    threshold = cfg.get("sgrad", "threshold" if variant == "nested" else "none") == "threshold"
+    # lambda (threshold rule) / gamma (custom loss): the thesis' operating points (chapter4.tex:106-113,225-226)
+    value = (1e-10 if mnist else 1e-11) if variant in ("nested", "paper") else 1e-9
     if cifar:
-        net = models.cifar_resnet18(0.0, seed=42, orientation="channelwise").cuda().train()
+        from learned_quantization_b200.paper_implementation.custom_components import custom_layers as pi
+        pi.set_scale_grad_mode("threshold" if threshold else "none")
+        net = models.cifar_resnet18(value if threshold else 0.0, seed=42, orientation="channelwise").cuda().train()
+        pi.set_scale_grad_mode("none")
+    elif mnist:
+        net = models.mnist_mlp(value, seed=42, orientation="scalar", variant=variant).cuda().train()
     else:
         net = models.imagenette_resnet(value, seed=42, orientation="channelwise", variant=variant,
                                        kernel_storage=args.qat_storage).cuda().train()
@@ -452,7 +608,6 @@ def run_qat(args, rank, world, local, model="imagenette"):
         x = x / 255.0
     with torch.no_grad():
         net(x[:2])                                    # builds the layers
-    comm = NcclComm() if world > 1 else None
     loss_fn = scce
     if variant == "custom_loss":                      # IMAGENETTE/custom_loss_terms/experiment.py:764-793
         import tempfile
@@ -462,16 +617,25 @@ def run_qat(args, rank, world, local, model="imagenette"):
         for h, _, _, _ in quantised_pairs(net):
             if h not in hosts:
                 hosts.append(h)
-        cls = {"maxbin": lf.SCCEMaxBin, "difference": lf.SCCEDifference, "inverse": lf.SCCEInverse}[args.qat_loss]
+        cls = {"maxbin": lf.SCCEMaxBin, "difference": lf.SCCEDifference, "inverse": lf.SCCEInverse}[cfg["loss"]]
         loss_obj = cls(layers=hosts, penalty_rate=value, log_dir=tempfile.mkdtemp(prefix="lq_bench_"))
         loss_obj.log_to_files = False                 # the reference's three tf.print(file://) per step: not timed here
         loss_fn = loss_obj.compute_total_loss
     if cifar:
-        logits_loss = lambda yt, logits: scce(yt, torch.softmax(logits, dim=-1))
-        step = TrainStep(net, logits_loss, optimizer="sgd", lr=0.1, momentum=0.9, nesterov=True, weight_decay=5e-4,
-                         comm=comm, ds_mode="exact")
+        loss_fn = lambda yt, logits: scce(yt, torch.softmax(logits, dim=-1))
+        opt = dict(optimizer="sgd", lr=0.1, momentum=0.9, nesterov=True, weight_decay=5e-4)
     else:
-        step = TrainStep(net, loss_fn, optimizer="adam", lr=1e-4, comm=comm, ds_mode="exact")
+        opt = dict(optimizer="adam", lr=1e-4)
+    comm, comm_note = make_comm(args, world)
+    try:
+        step = TrainStep(net, loss_fn, comm=comm, ds_mode="exact", **opt)
+    except lq.LqError as e:                            # peer memory unavailable: raised on every rank together
+        if world == 1 or args.qat_comm != "peer":
+            raise
+        args.qat_comm = "nccl"
+        comm, comm_note = make_comm(args, world)
+        comm_note += f" (peer-memory exchange unavailable: {e})"
+        step = TrainStep(net, loss_fn, comm=comm, ds_mode="exact", **opt)
     hx = x.cpu().pin_memory()
     hy = y.cpu().pin_memory()
 
@@ -529,34 +693,61 @@ def run_qat(args, rank, world, local, model="imagenette"):
         loss_host = float(loss)
     barrier()
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
-    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    # the gradient exchange alone (N > 1): K launches between two events on the step's stream
+    exch_ms = 0.0
+    if world > 1:
+        for _ in range(3):
+            step._exchange()
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(steps):
+            step._exchange()
+        x1.record()
+        barrier()
+        exch_ms = x0.elapsed_time(x1) / steps
+    t = torch.tensor([dev_ms, e2e_ms, exch_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, exch_ms = t.tolist()
     n_q = sum(p.numel() for p in step.bank.params)
+    name = {"imagenette": f"imagenette_resnet_{variant}_channelwise_224" + (f"_{cfg['loss']}" if variant == "custom_loss" else ""),
+            "cifar_paper": "cifar10_paper_resnet18_channelwise_32", "mnist": "mnist_mlp_nested_per_tensor"}[model]
+    peer = getattr(step, "_peer", False)
     out = {"metric": "qat_images_per_s", "value": batch * world / (dev_ms * 1e-3), "unit": "images/s",
            "ms_per_step": dev_ms, "steps": steps, "warmup": warm,
            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": hx.numel() * 4 + hy.numel() * 8, "d2h_bytes_per_step": 4},
-           "config": {"workload": "cifar10_paper_resnet18_channelwise_32" if cifar else
-                      f"imagenette_resnet_{variant}_channelwise_224" + (f"_{args.qat_loss}" if variant == "custom_loss" else ""),
-                      "per_gpu_batch": batch, "global_batch": batch * world,
+           "config": {"workload": name, "per_gpu_batch": batch, "global_batch": batch * world,
                       "optimizer": "sgd(0.1, 0.9, nesterov, weight decay 5e-4) fused with MinValueConstraint" if cifar else
                       "adam(1e-4) fused with l2 + MinValueConstraint",
-                      ("lambda" if variant in ("nested", "paper") else "gamma"): value,
+                      ("lambda" if variant in ("nested", "paper") else "gamma"): value if (threshold or variant == "custom_loss") else 0.0,
                       "quantised_tensors": len(step.bank.params), "quantised_elements": n_q,
-                      "scale_grad_mode": "none (STE: dX = dy, ds = zeros, PI:62-64)" if cifar else
-                      "exact (allreduce dy, then threshold backward on every rank)",
+                      "scale_grad_mode": ("threshold (NQ:62-118) on the gradient averaged over all ranks (exact mode)" if threshold
+                                          else "none (STE: dX = dy, ds = zeros, CL:61-62 / PI:62-64)"),
                       "conv_math": "cuDNN TF32 (TF 2.11 default), fp32 storage", "parallelism": f"dp{world}",
-                      "kernel_storage": "hwio" if cifar else
+                      "gradient_exchange": comm_note,
+                      "kernel_storage": "hwio" if (cifar or mnist) else
                       args.qat_storage + (" (logical HWIO, cuDNN channels-last order in memory)" if args.qat_storage == "ohwi" else ""),
-                      "launch": "eager" if args.qat_eager else "one CUDA graph per step"},
+                      "launch": "eager" if args.qat_eager else
+                      ("one CUDA graph per step" if (world == 1 or peer) else "three CUDA graphs per step around the NCCL call")},
            "allreduce_floats": step.bucket.n_exact,
-           "our_launches_per_step": {"lq_mt_fq_fwd": 1, "lq_mt_fq_bwd": 0 if cifar else 2,
+           "our_launches_per_step": {"lq_mt_fq_fwd": 1,
+                                     "lq_mt_fq_bwd": (2 if threshold else 0) if not peer else 0,
+                                     "lq_dpx_exchange": (2 if threshold else 1) if peer else 0,
                                      ("lq_opt_sgd" if cifar else "lq_opt_adam"): -(-len(step.table.params) // 56),
-                                     "lq_dp_allreduce": 1 if world > 1 else 0},
+                                     "lq_dp_allreduce": 1 if (world > 1 and not peer) else 0},
            "last_loss": loss_host}
+    if world > 1:
+        nbytes = step.bucket.n_exact * 4
+        out["exchange"] = {"ms": exch_ms, "bytes": nbytes,
+                           "busbw_GBps": 2.0 * (world - 1) / world * nbytes / (exch_ms * 1e-3) / 1e9,
+                           "what": "gradient exchange + scale backward alone, K launches between two events" if peer else
+                                   "ncclAllReduce + lq_mt_fq_bwd alone, K launches between two events"}
+        if peer and comm.timed_out():
+            raise SystemExit("bench.py: a rank timed out in the peer-memory gradient exchange")
     if comm is not None:
+        barrier()
         comm.close()
     return out
 
@@ -686,8 +877,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-qat", action="store_true", help="skip the QAT images/s section of the line")
     ap.add_argument("--only-qat", action="store_true", help="debug: run only the QAT section and print it")
-    ap.add_argument("--qat-model", default="imagenette", choices=["imagenette", "cifar_paper"],
+    ap.add_argument("--qat-config", default="qat", choices=sorted(QAT_CONFIGS),
                     help="with --only-qat: which training configuration to time")
+    ap.add_argument("--qat-comm", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange of the QAT step (fused peer-memory kernel, or ncclAllReduce)")
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")
     ap.add_argument("--qat-steps", type=int, default=20)
     ap.add_argument("--qat-warmup", type=int, default=5)

@@ -39,10 +39,12 @@ class COracle:
             self._scratch = np.empty(n, np.float32)
         return self._scratch
 
-    def fwd_bwd(self, P, s, dy, layout, lam):
-        """(q, y, ds) for flat fp32 arrays viewed as layout = (outer, C, inner)."""
+    def fwd_bwd(self, P, s, dy, layout, lam, out=None):
+        """(q, y, ds) for flat fp32 arrays viewed as layout = (outer, C, inner).  `out` = (q, y) buffers to
+        reuse (a timed loop passes them so that fresh pages are not faulted in on every pass -- TensorFlow's
+        allocator pools its output tensors too)."""
         n = P.size
-        q, y = np.empty(n, np.float32), np.empty(n, np.float32)
+        q, y = out if out is not None else (np.empty(n, np.float32), np.empty(n, np.float32))
         ds = np.empty(layout[1], np.float32)
         scratch = self._buf(5 * n)
         self.lib.lqo_fq_forward(P, s, *layout, scratch, q, y)

@@ -500,30 +500,14 @@ def test_mnist_training_steps_follow_the_oracle(lq):
     P = dict(zip(names, (t.detach().cpu().numpy().copy() for t in (net.d1.W, net.d1.b, net.d2.W, net.d2.b))))
     S = dict(zip(names, (q.scale.detach().cpu().numpy().copy() for q in
                          (net.d1.nested_q_w_layer, net.d1.nested_q_b_layer, net.d2.nested_q_w_layer, net.d2.nested_q_b_layer))))
-    mP = {k: np.zeros_like(v) for k, v in P.items()}; vP = {k: np.zeros_like(v) for k, v in P.items()}
-    mS = {k: np.zeros_like(v) for k, v in S.items()}; vS = {k: np.zeros_like(v) for k, v in S.items()}
+    from oracle.mnist_step import MnistOracle
+    ref = MnistOracle(P, S, variant="nested", value=lam, lr=lr)
+    P, S = ref.P, ref.S
     X = x.flatten(1).cpu().numpy().astype(np.float32)
     Y = y.cpu().numpy()
     step = TrainStep(net, scce, optimizer="adam", lr=lr)
     for it in range(1, 4):
-        # ---- oracle step
-        Q = {k: o.fq_forward(P[k], S[k]) for k in names}                       # (codes, fake-quantised)
-        yq = {k: Q[k][1] for k in names}
-        h = X @ yq["W1"] + yq["b1"]
-        a = np.maximum(h, 0)
-        z = a @ yq["W2"] + yq["b2"]
-        e = np.exp(z - z.max(axis=1, keepdims=True)); p = e / e.sum(axis=1, keepdims=True)
-        loss_ref = float(np.mean(-np.log(np.clip(p[np.arange(B), Y], 1e-7, 1 - 1e-7))))
-        dz = p.copy(); dz[np.arange(B), Y] -= 1; dz = (dz / B).astype(np.float32)
-        g = {"W2": a.T @ dz, "b2": dz.sum(0)}
-        dh = (dz @ yq["W2"].T) * (h > 0)
-        g["W1"], g["b1"] = X.T @ dh, dh.sum(0)
-        for k in names:
-            gk = g[k].astype(np.float32)
-            _, ds = o.nested_backward(gk, Q[k][0], Q[k][1], S[k], lam, accum="fp64")
-            P[k], mP[k], vP[k] = o.adam_step(P[k], gk, mP[k], vP[k], lr, it)
-            S[k], mS[k], vS[k] = o.adam_step(S[k], np.asarray(ds, np.float32).reshape(S[k].shape), mS[k], vS[k], lr, it,
-                                             min_value=o.SCALE_INIT)
+        loss_ref = ref.step(X, Y)              # oracle/mnist_step.py: the reference's step in numpy
         # ---- our step
         loss = float(step(x, y))
         assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref), (it, loss, loss_ref)
