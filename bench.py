@@ -500,36 +500,22 @@ def dp_selfcheck(args, rank, world):
     import torch
     import torch.distributed as dist
     import learned_quantization_b200 as lq
-    from learned_quantization_b200 import RandomNormal
     from learned_quantization_b200.custom_loss_terms.custom_components.custom_loss_functions import \
         sparse_categorical_crossentropy as scce
-    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    from learned_quantization_b200.training.models import SelfCheckNet
     from learned_quantization_b200.training.step import TrainStep
 
-    class Net(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            init = RandomNormal(seed=9)
-            self.c1 = nq.CustomConv2DLayer(seed=9, penalty_threshold=1e-3, orientation="channelwise", initializer=init,
-                                           filters=8, kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
-                                           regularizer=None, kernel_storage="ohwi")
-            self.fc = nq.CustomDenseLayer(seed=9, units=10, penalty_threshold=1e-3, orientation="rowwise",
-                                          initializer=init, name="fc", regularizer=None)
-
-        def forward(self, x):
-            return torch.softmax(self.fc(torch.relu(self.c1(x)).mean(dim=(1, 2))), dim=-1)
-
-    B, lr, steps = 2 * world, 1e-3, 2
+    B, lr, steps = 2 * world, 1e-3, 3          # step 1 exchanges in one go, steps 2-3 overlapped with the backward
     g = torch.Generator().manual_seed(11)
     x, y = torch.rand(B, 10, 10, 3, generator=g).cuda(), torch.randint(0, 10, (B,), generator=g).cuda()
 
     def build():
         torch.manual_seed(0)
-        net = Net().cuda()
+        net = SelfCheckNet().cuda()
         net(x[:1])
         gs = torch.Generator(device="cuda").manual_seed(3)
         with torch.no_grad():
-            for q in (net.c1.nested_q_k_layer, net.c1.nested_q_b_layer, net.fc.nested_q_w_layer, net.fc.nested_q_b_layer):
+            for q in net.quant_layers():
                 q.scale.copy_(torch.empty_like(q.scale).uniform_(5e-3, 2e-2, generator=gs))
         return net
 
@@ -556,6 +542,7 @@ def dp_selfcheck(args, rank, world):
         ok = torch.tensor([1 if (diff <= 0.02 * lr and identical and not timed_out) else 0], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         out.update(ok=bool(int(ok)), max_abs_diff_vs_single_device=diff, tolerance=0.02 * lr,
+                   overlapped_pieces=[len(getattr(step, "_early", [])), len(getattr(step, "_late", []))],
                    ranks_bit_identical=identical, timed_out=timed_out)
         comm.close()
     except lq.LqError as e:                       # raised on every rank together (PeerComm.allocate is collective)
@@ -628,7 +615,8 @@ def run_qat(args, rank, world, local, key="qat"):
         opt = dict(optimizer="adam", lr=1e-4)
     comm, comm_note = make_comm(args, world)
     try:
-        step = TrainStep(net, loss_fn, comm=comm, ds_mode="exact", **opt)
+        step = TrainStep(net, loss_fn, comm=comm, ds_mode="exact", overlap=not args.qat_no_overlap,
+                         late_blocks=args.qat_late_blocks, **opt)
     except lq.LqError as e:                            # peer memory unavailable: raised on every rank together
         if world == 1 or args.qat_comm != "peer":
             raise
@@ -879,6 +867,9 @@ def main():
     ap.add_argument("--only-qat", action="store_true", help="debug: run only the QAT section and print it")
     ap.add_argument("--qat-config", default="qat", choices=sorted(QAT_CONFIGS),
                     help="with --only-qat: which training configuration to time")
+    ap.add_argument("--qat-no-overlap", action="store_true", help="N > 1: exchange all gradients after the backward")
+    ap.add_argument("--qat-late-blocks", type=int, default=32,
+                    help="N > 1: grid of the exchange that is started while the backward is still running")
     ap.add_argument("--qat-comm", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange of the QAT step (fused peer-memory kernel, or ncclAllReduce)")
     ap.add_argument("--qat-batch", type=int, default=64, help="per-GPU batch of the QAT step (reference: 64)")

@@ -247,7 +247,11 @@ int lq_p2p_destroy(lq_p2p_t* p);
  * desc.dy, plain and ws (>= lq_workspace_bytes(descs, n, LQ_PHASE_BWD)) must lie in the arena; P, s, ds are
  * ordinary device pointers.  Reference rounding only (floor, no clamp).  Every rank must issue the same
  * sequence of calls; barrier epochs live on the device, so a call may be captured in a CUDA graph and
- * replayed.  lq_dpx_error reports (and synchronises for) the time-out flag a rank raises when a peer
+ * replayed.  channel (0..3): exchanges that may run at the same time on different streams (a step that
+ * starts exchanging its late layers while the backward is still producing the early ones) must use
+ * different channels, and the same channel for the same call on every rank; max_blocks (0 = default, two
+ * persistent blocks per SM) bounds the grid so that concurrent exchanges fit on the device together.
+ * lq_dpx_error reports (and synchronises for) the time-out flag a rank raises when a peer
  * does not show up within ~2 s. */
 typedef struct lq_dpx lq_dpx_t;
 int lq_dpx_create(int rank, int world, size_t arena_bytes, lq_dpx_t** out, void* out_handle64, void** out_arena);
@@ -257,8 +261,14 @@ int lq_dpx_connect(lq_dpx_t* x, const void* handles64_all);
  * on one device, launched on different streams with few enough blocks to be resident together) */
 int lq_dpx_connect_ptrs(lq_dpx_t* x, const void* const* arenas);
 int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, float* plain, int64_t n_plain,
-                    float penalty_threshold, int scale_grad_mode,
+                    float penalty_threshold, int scale_grad_mode, int channel, int max_blocks,
                     void* ws, size_t ws_bytes, lq_stream_t stream);
+/* Flat in-place mean all-reduce of flat[0, n) (inside the arena, 16-byte aligned, n a multiple of 4) on the copy
+ * engine: bulk asynchronous copies (TMA) stage one tile from every rank's arena in shared memory, a few warps add
+ * them in rank order, bulk stores send the mean to every rank.  The bytes in flight live in shared memory, so a
+ * few dozen blocks (max_blocks, 0 = 32) fill the NVLinks: this is the exchange a training step starts on a side
+ * stream while its backward is still computing.  Channels and epochs as for lq_dpx_exchange. */
+int lq_dpx_allreduce(lq_dpx_t* x, float* flat, int64_t n, int channel, int max_blocks, lq_stream_t stream);
 int lq_dpx_error(lq_dpx_t* x, int* out_flag);
 int lq_dpx_destroy(lq_dpx_t* x);
 

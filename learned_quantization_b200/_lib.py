@@ -87,7 +87,8 @@ SIGNATURES = {
     "lq_dpx_create": (_I, [_I, _I, _SZ, C.POINTER(_P), _P, C.POINTER(_P)]),
     "lq_dpx_connect": (_I, [_P, _P]),
     "lq_dpx_connect_ptrs": (_I, [_P, C.POINTER(_P)]),
-    "lq_dpx_exchange": (_I, [_P, _DESCS, _I, _P, _I64, _F, _I, _P, _SZ, _P]),
+    "lq_dpx_exchange": (_I, [_P, _DESCS, _I, _P, _I64, _F, _I, _I, _I, _P, _SZ, _P]),
+    "lq_dpx_allreduce": (_I, [_P, _P, _I64, _I, _I, _P]),
     "lq_dpx_error": (_I, [_P, C.POINTER(_I)]),
     "lq_dpx_destroy": (_I, [_P]),
 }

@@ -20,22 +20,26 @@
 // After the kernel every rank holds identical averaged gradients and identical partials; the ordinary
 // second stage (mt_finalize) then yields bit-identical ds everywhere with no further exchange.
 // A rank that waits ~2 s for a peer raises the error flag and gives up: a dead peer cannot hang the GPU.
+#include <stdlib.h>
 #include <string.h>
 #include "lq_fq_ops.cuh"
+#include "lq_col_tma.cuh"
 
 namespace lq {
 
 constexpr int kDpxMaxWorld = 8;
 constexpr int kDpxGridMax = 148 * 2;          // persistent blocks per rank (two resident per SM)
-constexpr size_t kDpxCtlBytes = 64 << 10;     // control region in front of the user arena
+constexpr int kDpxChannels = 4;               // exchanges that may be in flight at once (one per stream)
+constexpr size_t kDpxCtlBytes = 192 << 10;    // control region in front of the user arena
 
-// control region layout (bytes from the arena base):
-//   [0, 40K)   flags[2 phases][kDpxMaxWorld src][kDpxGridMax] u64   written by the peers (37 888 bytes)
-//   [40K, 44K) blk_epoch[kDpxGridMax] u64                           local only
-//   [44K]      err (int) ; [44K + 64] one (float 1.0f)              local only
-constexpr size_t kOffEpoch = 40 << 10, kOffErr = 44 << 10, kOffOne = (44 << 10) + 64;
-static_assert(2 * kDpxMaxWorld * kDpxGridMax * 8 <= kOffEpoch && kOffEpoch + kDpxGridMax * 8 <= kOffErr && kOffOne + 4 <= kDpxCtlBytes,
-              "control region layout");
+// control region layout (bytes from the arena base), per channel ch at ch * kChanBytes:
+//   [0, 37 888)        flags[2 phases][kDpxMaxWorld src][kDpxGridMax] u64   written by the peers
+//   [38 912, 41 280)   blk_epoch[kDpxGridMax] u64                           local only
+// then, once:  [kOffErr] err (int) ; [kOffOne] one (float 1.0f)             local only
+constexpr size_t kChanBytes = 44 << 10, kOffEpoch = 38 << 10;
+constexpr size_t kOffErr = kDpxChannels * kChanBytes, kOffOne = kOffErr + 64;
+static_assert(2 * kDpxMaxWorld * kDpxGridMax * 8 <= kOffEpoch && kOffEpoch + kDpxGridMax * 8 <= kChanBytes &&
+              kOffOne + 4 <= kDpxCtlBytes, "control region layout");
 
 struct DpxCtl {
   long long delta[kDpxMaxWorld];     // byte distance from a local arena address to rank r's mapping of it
@@ -199,6 +203,123 @@ __global__ void __launch_bounds__(kThreads, 2) dpx_kernel(const __grid_constant_
   if (threadIdx.x == 0) c.blk_epoch[blockIdx.x] = epoch;
 }
 
+// ------------------------------------------------------------------ flat mean all-reduce on the copy engine
+// The exchange that runs WHILE the backward is still computing must not take SMs away from the convolutions:
+// an NVLink round trip is several microseconds, so a kernel that keeps its bytes in flight in registers needs
+// hundreds of resident blocks to fill the links (measured: ~2 GB/s per 256-thread block).  Here the bytes in
+// flight live in shared memory instead: a block owns a ring of stages, one thread issues bulk asynchronous
+// copies (cp.async.bulk, the TMA engine) of one 8 KB tile from EVERY rank's arena into a stage, four warps add
+// the W tiles in rank order out of shared memory, and the mean goes back to every rank by bulk stores straight
+// from shared memory.  ~190 KB in flight per block at any world size: a couple of dozen blocks fill the links.
+// Tile t of the range belongs to rank t % W (reduce-scatter + all-gather of one tile in one pass); the same
+// two flag barriers as above bracket the data phase.
+constexpr int kArTile = 2048;                       // floats per tile (8 KB)
+constexpr int kArConsumers = 128;                   // 4 consumer warps; warp 0 is the producer
+constexpr int kArThreads = 32 + kArConsumers;
+constexpr int kArSmemBudget = 216 << 10;
+constexpr int kArMaxStages = 8;
+
+struct ArJob { float* flat; long long n; int stages; };
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kArThreads, 1) dpx_allreduce_kernel(const __grid_constant__ ArJob job,
+                                                                      const __grid_constant__ DpxCtl c) {
+  extern __shared__ __align__(128) unsigned char ar_smem[];
+  __shared__ unsigned long long full[kArMaxStages], empty[kArMaxStages];
+  __shared__ unsigned long long s_epoch;
+  const int W = c.world, S = job.stages;
+  const int t = threadIdx.x;
+  float* stage0 = reinterpret_cast<float*>(ar_smem);
+  const size_t stage_floats = (size_t)(W + 1) * kArTile;         // W input tiles, then the output tile
+
+  cudaGridDependencySynchronize();
+  if (t == 0) {
+    s_epoch = c.blk_epoch[blockIdx.x] + 1ull;
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  const bool ok = dpx_barrier(c, 0, epoch, true);                 // every rank's local gradients are complete
+  if (ok) {
+    const long long ntiles = (job.n + kArTile - 1) / kArTile;
+    // my tiles: t = rank + W * m, m = blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long long n_mine_all = (ntiles - c.rank + W - 1) / W;                    // tiles of this rank (ntiles > rank)
+    const long long n_my = (n_mine_all > (long long)blockIdx.x)
+        ? (n_mine_all - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;               // ... of this block
+    auto tile_of = [&](long long i) { return (long long)c.rank + (long long)W * ((long long)blockIdx.x + i * gridDim.x); };
+    auto tile_floats = [&](long long tl) { const long long r = job.n - tl * kArTile; return (int)(r < kArTile ? r : kArTile); };
+    if (t == 0) {
+      // producer: W bulk loads per tile, as far ahead as the ring allows
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (long long i = 0; i < n_my; ++i) {
+        const int st = (int)(i % S);
+        if (i >= S) mbar_wait(&empty[st], (unsigned)(((i / S) - 1) & 1));
+        const long long tl = tile_of(i);
+        const unsigned bytes = (unsigned)tile_floats(tl) * 4u;
+        mbar_expect_tx(&full[st], bytes * (unsigned)W);
+        float* dst = stage0 + (size_t)st * stage_floats;
+        const char* src = reinterpret_cast<const char*>(job.flat + tl * kArTile);
+        for (int r = 0; r < W; ++r) bulk_load(dst + (size_t)r * kArTile, src + c.delta[r], bytes, &full[st]);
+      }
+    } else if (t >= 32) {
+      const int ct = t - 32;
+      for (long long i = 0; i < n_my; ++i) {
+        const int st = (int)(i % S);
+        mbar_wait(&full[st], (unsigned)((i / S) & 1));
+        const long long tl = tile_of(i);
+        const int nf = tile_floats(tl);
+        float* in = stage0 + (size_t)st * stage_floats;
+        float* out = in + (size_t)W * kArTile;
+#pragma unroll
+        for (int u = 0; u < kArTile / 4 / kArConsumers; ++u) {
+          const int v = ct + u * kArConsumers;                     // float4 index inside the tile
+          if (4 * v < nf) {
+            float4 a = reinterpret_cast<const float4*>(in)[v];
+            for (int r = 1; r < W; ++r) {
+              const float4 b = reinterpret_cast<const float4*>(in + (size_t)r * kArTile)[v];
+              a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+            }
+            reinterpret_cast<float4*>(out)[v] = make_float4(__fmul_rn(a.x, c.inv), __fmul_rn(a.y, c.inv),
+                                                            __fmul_rn(a.z, c.inv), __fmul_rn(a.w, c.inv));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // my smem writes, before the bulk stores read them
+        asm volatile("bar.sync 1, %0;" ::"n"(kArConsumers) : "memory");
+        if (ct == 0) {
+          char* gdst = reinterpret_cast<char*>(job.flat + tl * kArTile);
+          for (int r = 0; r < W; ++r) bulk_store(gdst + c.delta[r], out, (unsigned)nf * 4u);
+          bulk_commit();
+          if (i >= 1) { bulk_wait_read1(); mbar_arrive(&empty[(int)((i - 1) % S)]); }   // tile i-1's stores have read their stage
+        }
+      }
+      if (ct == 0) {
+        bulk_wait0();                                             // every store of mine is complete
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+    }
+  } else if (t == 0) {
+    atomicExch(c.err, 1);
+  }
+  __threadfence_system();
+  __syncthreads();
+  const bool ok2 = dpx_barrier(c, 1, epoch, ok);                  // every rank has finished storing into my arena
+  if (!ok2 && ok && t == 0) atomicExch(c.err, 1);
+  if (t == 0) c.blk_epoch[blockIdx.x] = epoch;
+}
+
 }  // namespace lq
 
 using namespace lq;
@@ -276,9 +397,12 @@ static int dpx_launch(unsigned grid, const JobTable& tab, const PeerBwdOp& op, c
 }
 
 extern "C" int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, float* plain, int64_t n_plain,
-                               float penalty_threshold, int scale_grad_mode,
+                               float penalty_threshold, int scale_grad_mode, int channel, int max_blocks,
                                void* ws, size_t ws_bytes, lq_stream_t stream) {
   if (!x) { set_error("lq_dpx_exchange: null handle"); return LQ_E_NULLPTR; }
+  if (channel < 0 || channel >= kDpxChannels || max_blocks < 0) {
+    set_error("lq_dpx_exchange: channel must be in [0, %d), max_blocks >= 0", kDpxChannels); return LQ_E_BADMODE;
+  }
   if (!x->connected) { set_error("lq_dpx_exchange: lq_dpx_connect has not been called"); return LQ_E_BADMODE; }
   if (n < 0 || n_plain < 0) { set_error("lq_dpx_exchange: negative count"); return LQ_E_BADSHAPE; }
   if ((n && !descs) || (n_plain && !plain)) { set_error("lq_dpx_exchange: null descs / plain"); return LQ_E_NULLPTR; }
@@ -344,13 +468,18 @@ extern "C" int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, 
   if (total) {
     DpxCtl c{};
     for (int r = 0; r < x->world; ++r) c.delta[r] = static_cast<char*>(x->peer[r]) - ctl;
-    c.flags = reinterpret_cast<unsigned long long*>(ctl);
-    c.blk_epoch = reinterpret_cast<unsigned long long*>(ctl + kOffEpoch);
+    c.flags = reinterpret_cast<unsigned long long*>(ctl + (size_t)channel * kChanBytes);
+    c.blk_epoch = reinterpret_cast<unsigned long long*>(ctl + (size_t)channel * kChanBytes + kOffEpoch);
     c.err = reinterpret_cast<int*>(ctl + kOffErr);
     c.rank = x->rank; c.world = x->world; c.total = total;
     c.inv = 1.0f / (float)x->world;
     const unsigned mine = (total + (unsigned)x->world - 1) / (unsigned)x->world;
-    const unsigned grid = mine < (unsigned)kDpxGridMax ? (mine ? mine : 1u) : (unsigned)kDpxGridMax;
+    unsigned cap = (max_blocks > 0 && max_blocks < kDpxGridMax) ? (unsigned)max_blocks : (unsigned)kDpxGridMax;
+    if (const char* e = getenv("LQ_DPX_GRID")) {          // tuning knob (tools/dpx_probe.py); must agree on every rank
+      const long v = strtol(e, nullptr, 10);
+      if (v >= 1 && v <= (long)cap) cap = (unsigned)v;
+    }
+    const unsigned grid = mine < cap ? (mine ? mine : 1u) : cap;
     PeerBwdOp op;
     static_cast<BwdThresholdOp<false>&>(op) = make_bwd_op<false>(qm, penalty_threshold);
     switch (x->world) {
@@ -368,6 +497,49 @@ extern "C" int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, 
     if (descs[i].ds && descs[i].C > 0)
       if ((rc = cuda_fail(cudaMemsetAsync(descs[i].ds, 0, (size_t)descs[i].C * 4, st), "ds = 0"))) return rc;
   return LQ_OK;
+}
+
+static DpxCtl make_ctl(const lq_dpx* x, int channel) {
+  char* ctl = static_cast<char*>(x->base);
+  DpxCtl c{};
+  for (int r = 0; r < x->world; ++r) c.delta[r] = static_cast<char*>(x->peer[r]) - ctl;
+  c.flags = reinterpret_cast<unsigned long long*>(ctl + (size_t)channel * kChanBytes);
+  c.blk_epoch = reinterpret_cast<unsigned long long*>(ctl + (size_t)channel * kChanBytes + kOffEpoch);
+  c.err = reinterpret_cast<int*>(ctl + kOffErr);
+  c.rank = x->rank; c.world = x->world;
+  c.inv = 1.0f / (float)x->world;
+  return c;
+}
+
+extern "C" int lq_dpx_allreduce(lq_dpx_t* x, float* flat, int64_t n, int channel, int max_blocks, lq_stream_t stream) {
+  if (!x) { set_error("lq_dpx_allreduce: null handle"); return LQ_E_NULLPTR; }
+  if (!x->connected) { set_error("lq_dpx_allreduce: lq_dpx_connect has not been called"); return LQ_E_BADMODE; }
+  if (channel < 0 || channel >= kDpxChannels || max_blocks < 0) {
+    set_error("lq_dpx_allreduce: channel must be in [0, %d), max_blocks >= 0", kDpxChannels); return LQ_E_BADMODE;
+  }
+  if (n < 0) { set_error("lq_dpx_allreduce: n < 0"); return LQ_E_BADSHAPE; }
+  if (n == 0) return LQ_OK;
+  if (!flat) { set_error("lq_dpx_allreduce: null buffer"); return LQ_E_NULLPTR; }
+  if (!aligned16(flat) || (n & 3)) { set_error("lq_dpx_allreduce: the range must be 16-byte aligned and a multiple of 4 floats"); return LQ_E_BADSHAPE; }
+  if (!in_arena(x, flat, (size_t)n * 4)) { set_error("lq_dpx_allreduce: the range lies outside the arena"); return LQ_E_BADSHAPE; }
+  ArJob job{};
+  job.flat = flat; job.n = n;
+  const size_t stage_bytes = (size_t)(x->world + 1) * kArTile * 4;
+  job.stages = (int)(kArSmemBudget / stage_bytes);
+  if (job.stages > kArMaxStages) job.stages = kArMaxStages;
+  if (job.stages < 2) { set_error("lq_dpx_allreduce: world too large for the shared-memory ring"); return LQ_E_BADSHAPE; }
+  const size_t smem = (size_t)job.stages * stage_bytes;
+  DpxCtl c = make_ctl(x, channel);
+  const long long ntiles = (n + kArTile - 1) / kArTile;
+  const long long per_rank = (ntiles + x->world - 1) / x->world;
+  long long grid = max_blocks > 0 ? max_blocks : 32;
+  if (grid > kDpxGridMax) grid = kDpxGridMax;
+  if (grid > per_rank) grid = per_rank;
+  if (grid < 1) grid = 1;
+  cudaError_t e = cudaFuncSetAttribute(dpx_allreduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "dpx_allreduce smem attribute");
+  dpx_allreduce_kernel<<<dim3((unsigned)grid), dim3(kArThreads), smem, (cudaStream_t)stream>>>(job, c);
+  return cuda_fail(cudaGetLastError(), "dpx_allreduce launch");
 }
 
 extern "C" int lq_dpx_error(lq_dpx_t* x, int* out_flag) {

@@ -197,18 +197,27 @@ class PeerComm(Comm):
         return self.arena
 
     def exchange(self, descs, n: int, plain: Optional[torch.Tensor], penalty_threshold: float, scale_grad_mode: int,
-                 ws: Optional[torch.Tensor]) -> None:
-        """mean-allreduce of every desc.dy and of `plain` (in place) + the scale gradients of the averaged dy."""
+                 ws: Optional[torch.Tensor], channel: int = 0, max_blocks: int = 0) -> None:
+        """mean-allreduce of every desc.dy and of `plain` (in place) + the scale gradients of the averaged dy.
+        Exchanges in flight at the same time (different streams) take different channels."""
         check(lib.lq_dpx_exchange(self._h, descs, n,
                                   None if plain is None or plain.numel() == 0 else plain.data_ptr(),
                                   0 if plain is None else plain.numel(), float(penalty_threshold), int(scale_grad_mode),
+                                  int(channel), int(max_blocks),
                                   None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(),
                                   torch.cuda.current_stream().cuda_stream))
 
-    def allreduce_mean_(self, flat: torch.Tensor) -> None:
+    def allreduce_mean_(self, flat: torch.Tensor, channel: int = 0) -> None:
         """Plain in-place mean all-reduce of a slice of the arena."""
         if flat.numel():
-            self.exchange(None, 0, flat, 0.0, _lib.LQ_SGRAD_NONE, None)
+            self.exchange(None, 0, flat, 0.0, _lib.LQ_SGRAD_NONE, None, channel)
+
+    def allreduce_dma_(self, flat: torch.Tensor, channel: int = 0, max_blocks: int = 0) -> None:
+        """The same mean all-reduce on the copy engine (lq_dpx_allreduce): bulk asynchronous copies through
+        shared memory, a few dozen blocks -- the variant to run beside other kernels."""
+        if flat.numel():
+            check(lib.lq_dpx_allreduce(self._h, flat.data_ptr(), flat.numel(), int(channel), int(max_blocks),
+                                       torch.cuda.current_stream().cuda_stream))
 
     def timed_out(self) -> bool:
         flag = C.c_int(0)

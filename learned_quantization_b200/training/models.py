@@ -205,6 +205,32 @@ class CifarResNet18(nn.Module):
         return self.fc(x.mean(dim=(1, 2)))           # logits, as in the reference (resnet.py:126-137)
 
 
+class SelfCheckNet(nn.Module):
+    """A small BatchNorm-free model on the nested layers (two quantised convs of different storage orders and a
+    quantised dense layer: interleaved (COL) and per-tensor layouts, an early and a late piece of the gradient exchange):
+    without batch statistics, `world` ranks with a shard of a batch each must end a step where one device with
+    the whole batch ends it.  Used by bench.py's pre-timing self-check and tests/test_gpu_dp.py."""
+
+    def __init__(self, penalty_threshold: float = 1e-3, seed: int = 9):
+        super().__init__()
+        from ..nested_quantization_layer.custom_components import custom_layers as nq
+        init = RandomNormal(seed=seed)
+        mk = lambda f, nm, st: nq.CustomConv2DLayer(seed=seed, penalty_threshold=penalty_threshold, orientation="channelwise",
+                                                    initializer=init, filters=f, kernel_size=(3, 3), strides=(1, 1),
+                                                    padding="same", name=nm, regularizer=None, kernel_storage=st)
+        self.c1, self.c2 = mk(8, "a", "ohwi"), mk(32, "b", "hwio")
+        self.fc = nq.CustomDenseLayer(seed=seed, units=10, penalty_threshold=penalty_threshold, orientation="rowwise",
+                                      initializer=init, name="fc", regularizer=None)
+
+    def forward(self, x):
+        x = torch.relu(self.c2(torch.relu(self.c1(x))))
+        return torch.softmax(self.fc(x.mean(dim=(1, 2))), dim=-1)
+
+    def quant_layers(self):
+        return (self.c1.nested_q_k_layer, self.c1.nested_q_b_layer, self.c2.nested_q_k_layer, self.c2.nested_q_b_layer,
+                self.fc.nested_q_w_layer, self.fc.nested_q_b_layer)
+
+
 def mnist_mlp(value, seed=42, orientation="rowwise", variant="nested"):
     return MnistMLP(value, seed, orientation, variant)
 

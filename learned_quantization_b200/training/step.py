@@ -98,7 +98,12 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, loss_fn: Callable, *, optimizer: str = "adam", lr: float = 1e-4,
                  momentum: float = 0.0, nesterov: bool = False, weight_decay: float = 0.0,
-                 comm: Optional[Comm] = None, ds_mode: str = "exact"):
+                 comm: Optional[Comm] = None, ds_mode: str = "exact", overlap: bool = True, late_blocks: int = 32):
+        """overlap (PeerComm, exact mode): start exchanging the late layers' gradients on a side stream as soon
+        as the backward has produced them, while it is still working on the early layers.  late_blocks: grid of
+        that early-started exchange -- it waits on NVLink, not on arithmetic, so it is given few SMs and a long
+        time (hidden behind the rest of the backward) instead of many SMs taken away from the convolutions."""
+        self.late_blocks = int(late_blocks)
         self.model, self.loss_fn = model, loss_fn
         self.comm = comm or SingleComm()
         self.ds_mode = ds_mode
@@ -108,25 +113,48 @@ class TrainStep:
         self.plain = [p for p in model.parameters() if id(p) not in quant_ids and p.requires_grad]
         dev = b.params[0].device
         self._peer = isinstance(self.comm, PeerComm)
-        self._xws = None
         alloc = None
         if self._peer:
-            # the bucket and the partial workspace of the fused exchange live in the peer-mapped arena
-            ws_bytes = ops.workspace_bytes([ops.make_desc(layout=l) for l in b.layouts], _lib.LQ_PHASE_BWD)
+            # The exchange runs in (at most) two pieces.  LATE = the tensors at the end of the model holding ~90 %
+            # of the elements: the backward produces their gradients first, so their exchange can start while the
+            # early layers' backward is still running.  EARLY = the rest, plus the plain gradients.
+            n = len(b.params)
+            sizes = [p.numel() for p in b.params]
+            k = n
+            while k > 0 and sum(sizes[k:]) < 0.9 * sum(sizes):
+                k -= 1
+            if not (overlap and ds_mode == "exact" and self.comm.world > 1 and 0 < k < n):
+                k = 0                                  # one piece
+            self._late, self._early = list(range(k, n)), list(range(0, k))
+            ws_of = lambda idx: -(-max(ops.workspace_bytes([ops.make_desc(layout=b.layouts[i]) for i in idx],
+                                                          _lib.LQ_PHASE_BWD), 256) // 256) * 256
+            ws_late, ws_early = ws_of(self._late), ws_of(self._early)
 
             def alloc(n_floats):
+                # the bucket and the partial workspaces of the fused exchange live in the peer-mapped arena
                 nb = -(-n_floats * 4 // 256) * 256
-                arena = self.comm.allocate(nb + max(ws_bytes, 256))
-                self._xws = arena[nb:]
+                arena = self.comm.allocate(nb + ws_late + ws_early)
+                self._xws = {"late": arena[nb:nb + ws_late], "early": arena[nb + ws_late:]}
                 return arena[:n_floats * 4].view(torch.float32)
         self.bucket = GradBucket(list(b.params), [p.shape for p in self.plain], [s.shape for s in b.scales], dev,
                                  alloc=alloc)
         if self._peer:
             threshold = b.sgrad_mode == _lib.LQ_SGRAD_THRESHOLD
-            self._xdescs = ops.desc_array([
-                ops.make_desc(P=p.data, s=s.data, dy=dy, ds=(ds if threshold else None), layout=l)
-                for p, s, dy, ds, l in zip(b.params, b.scales, self.bucket.dy, self.bucket.ds, b.layouts)])
+            descs = lambda idx: ops.desc_array([
+                ops.make_desc(P=b.params[i].data, s=b.scales[i].data, dy=self.bucket.dy[i],
+                              ds=(self.bucket.ds[i] if threshold else None), layout=b.layouts[i]) for i in idx])
+            self._xdescs = {"late": descs(self._late), "early": descs(self._early)}
             self._xplain = self.bucket.flat[self.bucket.plain_begin:self.bucket.n_exact]
+            self._side = torch.cuda.Stream(priority=-1)     # its few blocks are placed ahead of the backward's
+            lo = self.bucket.dy[self._late[0]].data_ptr() - self.bucket.flat.data_ptr()
+            self._late_range = self.bucket.flat[lo // 4:self.bucket.plain_begin]
+            self._armed = False          # hooks act only inside _forward_backward
+            self._late_done = False      # the LATE piece has been launched on the side stream in this step
+            self._pending = 0
+            self._direct_grads = None    # does the loss act on P / s directly (loss-term penalties)? known after step 1
+            if self._early:
+                for i in self._late:
+                    b.ys[i].register_post_accumulate_grad_hook(self._on_late_grad)
         # optimizer table over [P | plain | s], gradients = the bucket views (pointers never change)
         l2 = []
         for host in b.hosts:
@@ -162,17 +190,64 @@ class TrainStep:
         for t in b.params + b.scales:
             t.grad = None
         loss = self.loss_fn(y_true, self.model(x)).mean()
-        loss.backward()
+        split = self._peer and bool(self._early) and self._overlap_ok()
+        if split:
+            self._main = torch.cuda.current_stream()
+            self._pending, self._late_done, self._armed = len(self._late), False, True
+        try:
+            loss.backward()
+        finally:
+            if self._peer:
+                self._armed = False
         with torch.no_grad():
-            torch._foreach_copy_(bucket.dy, [y.grad for y in b.ys])
+            rest = self._early if (split and self._late_done) else range(len(b.ys))
+            torch._foreach_copy_([bucket.dy[i] for i in rest], [b.ys[i].grad for i in rest])
             if self.plain:
                 torch._foreach_copy_(bucket.plain, [p.grad for p in self.plain])
-            # loss terms that act on P / s directly (custom_loss_terms penalties): identical on every
-            # rank, so adding them before the mean-allreduce leaves them unchanged
-            extra_p = [(v, p.grad) for v, p in zip(bucket.dy, b.params) if p.grad is not None]
-            if extra_p:
-                torch._foreach_add_([v for v, _ in extra_p], [g for _, g in extra_p])
+            # loss terms that act on P / s directly (custom_loss_terms penalties) are identical on every rank:
+            # adding them before or after the mean over ranks is the same thing.  They go in before it, except
+            # when the LATE piece is already being exchanged (then _exchange adds them after the join).
+            self._extra_p = [(v, p.grad) for v, p in zip(bucket.dy, b.params) if p.grad is not None]
+            if self._peer and self._direct_grads is None:
+                self._direct_grads = bool(self._extra_p) or any(s.grad is not None for s in b.scales)
+            if self._extra_p and not (split and self._late_done):
+                torch._foreach_add_([v for v, _ in self._extra_p], [g for _, g in self._extra_p])
+                self._extra_p = []
         return loss.detach()
+
+    # ------------------------------------------------------------------ overlapped exchange (PeerComm)
+    def _overlap_ok(self) -> bool:
+        """The early launch is taken from the second step on, and never when the threshold rule must see
+        gradients that the loss adds to P directly (they are only known after the backward)."""
+        if self._direct_grads is None:
+            return False
+        return not (self._direct_grads and self.bank.sgrad_mode == _lib.LQ_SGRAD_THRESHOLD)
+
+    def _on_late_grad(self, _y) -> None:
+        """post-accumulate hook of the LATE tensors (runs on the autograd thread during loss.backward()):
+        when the last of them has its gradient, fork the side stream and exchange the piece there."""
+        if not self._armed:
+            return
+        self._pending -= 1
+        if self._pending != 0:
+            return
+        b, bucket = self.bank, self.bucket
+        ev = torch.cuda.Event()
+        ev.record(self._main)                        # everything the backward has enqueued so far
+        self._side.wait_event(ev)
+        with torch.no_grad(), torch.cuda.stream(self._side):
+            torch._foreach_copy_([bucket.dy[i] for i in self._late], [b.ys[i].grad for i in self._late])
+            # beside the convolutions: the copy-engine all-reduce (few blocks, bytes in flight in shared memory);
+            # the scale backward of these tensors follows on the main stream after the join (_exchange)
+            self.comm.allreduce_dma_(self._late_range, channel=1, max_blocks=self.late_blocks)
+        self._late_done = True
+
+    def _exchange_piece(self, which: str) -> None:
+        b = self.bank
+        d = self._xdescs[which]
+        early = which == "early" or not self._early       # the piece that carries the plain gradients
+        self.comm.exchange(d if len(d) else None, len(d), self._xplain if early else None, b.lam, b.sgrad_mode,
+                           self._xws[which], channel=(0 if early else 1))
 
     def _update(self):
         """penalty scale gradients, then the fused optimizer + constraint."""
@@ -194,9 +269,22 @@ class TrainStep:
             if not self._peer:
                 exchange_gradients(self.bucket, self.comm, scale_backward, self.ds_mode)
             elif self.ds_mode == "exact":
-                # ONE kernel: mean of [dy | plain] over the ranks' arenas + the threshold backward of the mean
+                # ONE kernel per piece: mean of [dy | plain] over the ranks' arenas + the threshold backward of the mean
                 b = self.bank
-                self.comm.exchange(self._xdescs, len(self._xdescs), self._xplain, b.lam, b.sgrad_mode, self._xws)
+                if self._early and not self._late_done:
+                    self._exchange_piece("late")          # not launched early (first step, or called on its own)
+                self._exchange_piece("early" if self._early else "late")
+                if self._late_done:
+                    torch.cuda.current_stream().wait_stream(self._side)
+                    self._late_done = False
+                    if b.sgrad_mode == _lib.LQ_SGRAD_THRESHOLD:      # NQ:62-118 on the averaged gradients of the late tensors
+                        L = self._late
+                        ops.mt_fq_bwd([self.bucket.dy[i] for i in L], [b.params[i].data for i in L],
+                                      [b.scales[i].data for i in L], [self.bucket.ds[i] for i in L], b.lam,
+                                      [b.layouts[i] for i in L], scale_grad_mode=b.sgrad_mode)
+                if getattr(self, "_extra_p", None):
+                    torch._foreach_add_([v for v, _ in self._extra_p], [g for _, g in self._extra_p])
+                    self._extra_p = []
                 if b.sgrad_mode == _lib.LQ_SGRAD_NONE:
                     self.bucket.flat[self.bucket.n_exact:self.bucket.n_total].zero_()
             elif self.ds_mode == "local":

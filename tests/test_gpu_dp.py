@@ -15,29 +15,15 @@ LR, STEPS, B = 1e-3, 2, 8
 
 
 def _net():
-    from learned_quantization_b200 import RandomNormal
-    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
-
-    class Net(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            init = RandomNormal(seed=9)
-            self.c1 = nq.CustomConv2DLayer(seed=9, penalty_threshold=1e-3, orientation="channelwise", initializer=init,
-                                           filters=8, kernel_size=(3, 3), strides=(1, 1), padding="same", name="a",
-                                           regularizer=None, kernel_storage="ohwi")
-            self.fc = nq.CustomDenseLayer(seed=9, units=10, penalty_threshold=1e-3, orientation="rowwise", initializer=init,
-                                          name="fc", regularizer=None)
-
-        def forward(self, x):
-            return torch.softmax(self.fc(torch.relu(self.c1(x)).mean(dim=(1, 2))), dim=-1)
-    return Net()
+    from learned_quantization_b200.training.models import SelfCheckNet
+    return SelfCheckNet()
 
 
 def _prepare(net, x):
     net(x[:1])
     g = torch.Generator(device="cuda").manual_seed(3)
     with torch.no_grad():
-        for q in (net.c1.nested_q_k_layer, net.c1.nested_q_b_layer, net.fc.nested_q_w_layer, net.fc.nested_q_b_layer):
+        for q in net.quant_layers():
             q.scale.copy_(torch.empty_like(q.scale).uniform_(5e-3, 2e-2, generator=g))
 
 
@@ -67,6 +53,7 @@ def _worker(rank, world, port, out_path, kind="nccl", graph_steps=0):
     if graph_steps:                 # capture() runs 3 eager steps itself; the rest are replays of ONE graph
         step.capture(x[lo:hi].contiguous(), y[lo:hi].contiguous(), warmup=3)
         assert len(step._graph) == (1 if kind == "peer" else 3)
+        assert kind != "peer" or (step._early and step._late)      # the exchange runs in two overlapped pieces
         for _ in range(graph_steps - 3):
             step.replay(x[lo:hi], y[lo:hi])
     else:

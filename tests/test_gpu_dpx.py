@@ -92,13 +92,13 @@ def fill(ranks, sizes, rng):
     return out
 
 
-def launch(lq, rk, Ps, ss, layouts, sizes, dss, mode):
+def launch(lq, rk, Ps, ss, layouts, sizes, dss, mode, channel=0):
     ops = lq.ops
     descs = ops.desc_array([ops.make_desc(P=p, s=s, dy=rk.view(i, n), ds=ds, layout=l)
                             for i, (p, s, n, ds, l) in enumerate(zip(Ps, ss, sizes, dss, layouts))])
     plain = rk.view(len(sizes), N_PLAIN)
     with torch.cuda.stream(rk.stream):
-        rk.check(rk.lib.lq_dpx_exchange(rk.h, descs, len(descs), plain.data_ptr(), N_PLAIN, LAM, mode,
+        rk.check(rk.lib.lq_dpx_exchange(rk.h, descs, len(descs), plain.data_ptr(), N_PLAIN, LAM, mode, channel, 0,
                                         rk.ws.data_ptr(), rk.ws.numel(), rk.stream.cuda_stream))
     return descs
 
@@ -231,12 +231,49 @@ def test_arguments_are_checked(lq):
         ds = torch.empty_like(ss[0])
         d = ops.desc_array([ops.make_desc(P=Ps[0], s=ss[0], dy=outside, ds=ds, layout=layouts[0])])
         with pytest.raises(LqError, match="outside the arena"):
-            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, rk.ws.data_ptr(), rk.ws.numel(), 0))
+            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, 0, 0, rk.ws.data_ptr(), rk.ws.numel(), 0))
         d = ops.desc_array([ops.make_desc(P=Ps[0], s=ss[0], dy=rk.view(0, sizes[0]), dX=outside, ds=ds, layout=layouts[0])])
         with pytest.raises(LqError, match="in place"):
-            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, rk.ws.data_ptr(), rk.ws.numel(), 0))
+            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, 0, 0, rk.ws.data_ptr(), rk.ws.numel(), 0))
         d = ops.desc_array([ops.make_desc(P=Ps[0], s=ss[0], dy=rk.view(0, sizes[0]), ds=ds, layout=layouts[0])])
         with pytest.raises(LqError, match="workspace"):
-            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, rk.ws.data_ptr(), 16, 0))
+            rk.check(rk.lib.lq_dpx_exchange(rk.h, d, 1, None, 0, LAM, 1, 0, 0, rk.ws.data_ptr(), 16, 0))
     finally:
         rk.close()
+
+
+@pytest.mark.parametrize("world,n", [(1, 4096), (2, 2048 * 5 + 12), (3, 2048 * 40 + 4), (4, 1000), (8, 2048 * 19 + 2044)])
+def test_copy_engine_allreduce_is_the_rank_order_mean(lq, world, n):
+    """lq_dpx_allreduce: bulk asynchronous copies through a shared-memory ring; same bits as the register kernel."""
+    from learned_quantization_b200._lib import check, lib
+    from learned_quantization_b200.training.dp import _DeviceSpan
+    rng = np.random.default_rng(200 + world)
+    hs, bases, flats, streams = [], [], [], []
+    try:
+        for r in range(world):
+            h, handle, base = C.c_void_p(), C.create_string_buffer(64), C.c_void_p()
+            check(lib.lq_dpx_create(r, world, n * 4 + 256, C.byref(h), handle, C.byref(base)))
+            hs.append(h); bases.append(base.value)
+            flats.append(torch.as_tensor(_DeviceSpan(base.value, n * 4, None), device="cuda:0").view(torch.float32))
+            streams.append(torch.cuda.Stream())
+        ptrs = (C.c_void_p * world)(*bases)
+        for h in hs:
+            check(lib.lq_dpx_connect_ptrs(h, ptrs))
+        for rep in range(3):                       # more tiles than stages on the second and third pass too
+            local = [rng.normal(0, 1e-3, size=n).astype(np.float32) for _ in range(world)]
+            for f, a in zip(flats, local):
+                f.copy_(torch.from_numpy(a))
+            torch.cuda.synchronize()
+            for h, f, st in zip(hs, flats, streams):
+                check(lib.lq_dpx_allreduce(h, f.data_ptr(), n, 2, 2, st.cuda_stream))     # channel 2, two blocks per rank
+            torch.cuda.synchronize()
+            want = mean_in_rank_order(local)
+            for r, (h, f) in enumerate(zip(hs, flats)):
+                flag = C.c_int(0)
+                check(lib.lq_dpx_error(h, C.byref(flag)))
+                assert flag.value == 0, "a rank timed out"
+                assert bits_equal(f.cpu().numpy(), want), (rep, r)
+    finally:
+        torch.cuda.synchronize()
+        for h in hs:
+            check(lib.lq_dpx_destroy(h))
