@@ -626,6 +626,13 @@ def run_qat(args, rank, world, local, key="qat"):
         step = TrainStep(net, loss_fn, comm=comm, ds_mode="exact", **opt)
     hx = x.cpu().pin_memory()
     hy = y.cpu().pin_memory()
+    if args.qat_skip_exchange and world > 1:          # diagnostic only: N independent replicas, nothing exchanged
+        def local_only(scale_backward=None):
+            with torch.no_grad():
+                (scale_backward or step._scale_backward)()
+        step._exchange = local_only
+        step._early = []
+        comm_note = "DIAGNOSTIC: no gradient exchange (independent replicas)"
 
     def barrier():
         if world > 1:
@@ -867,6 +874,7 @@ def main():
     ap.add_argument("--only-qat", action="store_true", help="debug: run only the QAT section and print it")
     ap.add_argument("--qat-config", default="qat", choices=sorted(QAT_CONFIGS),
                     help="with --only-qat: which training configuration to time")
+    ap.add_argument("--qat-skip-exchange", action="store_true", help="diagnostic: N > 1 without any gradient exchange")
     ap.add_argument("--qat-no-overlap", action="store_true", help="N > 1: exchange all gradients after the backward")
     ap.add_argument("--qat-late-blocks", type=int, default=32,
                     help="N > 1: grid of the exchange that is started while the backward is still running")

@@ -210,6 +210,7 @@ Job make_job(const Geom& g, const float* P, const float* s, const float* dy, flo
   j.regime = g.regime; j.vec = g.vec_ok; j.seg = g.seg; j.nseg = g.nseg;
   j.bx = g.bx; j.by = g.by; j.rpc = g.rpc; j.codes_dtype = codes_dtype;
   j.stream_hint = (g.n * 4 > kStreamBytes) ? 1 : 0;
+  j.n = g.n;
   j.write_dx = (dX != nullptr && dX != dy) ? 1 : 0;
   j.block_begin = 0; j.nblocks = (unsigned)g.nblocks;
   j.fast32 = (g.regime == REG_ROW && g.units < (1ll << 31) && g.C < (1ll << 31)) ? 1 : 0;

@@ -15,8 +15,33 @@ struct PenCtx { Recip rc; float4 aux; float k0, k1, k2; };
 
 __device__ __forceinline__ float sgn(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 
-// MaxBin forward: per group max_j(|P_j| / s) and how many elements attain it (the tie
-// count _MinOrMaxGrad divides by).  acc.c = max, acc.b = ties.
+// is this element one of the group's maxima?  lo >= 0: |p| >= lo (fast regime); otherwise compare quotients
+__device__ __forceinline__ unsigned tie_hit(float p, float lo, float mb, float sc) {
+  const float ap = fabsf(p);
+  return (lo >= 0.f) ? (ap >= lo ? 1u : 0u) : (__fdiv_rn(ap, sc) == mb ? 1u : 0u);
+}
+
+// ---- the fast regime of the loss-term passes (what makes them HBM-bound instead of issue-bound)
+// Both reductions can be carried out on |P| alone when the group's scale is an ordinary positive number:
+//  * MaxBin (LF:90-94): division by s > 0 is monotone, so max_j RN(|P_j| / s) = RN(max_j |P_j| / s): the element
+//    pass keeps max |P| (ONE instruction per element) and the second stage divides once per group.  The tie
+//    count TF's _MinOrMaxGrad needs is the number of elements whose QUOTIENT equals the maximum; those are the
+//    elements with |P_j| >= lo, lo = the smallest float whose quotient still rounds to the maximum (at most a
+//    few ulps below max |P|, found in the second stage by stepping down).  They are counted by pen_ties_kernel,
+//    which re-reads only the units whose own maximum reaches lo (normally one unit per group).
+//  * Difference (LF:175-178): |P - RN(P/s)| = |P| |1 - 1/s| (1 + e) with |e| <= 3 * 2^-24 whenever s <= 1/2 or
+//    s >= 2 (the two roundings are each 2^-24 relative to |P/s| and |d|, and |P/s| <= 2 |d| there), so the
+//    element pass keeps sum |P| and the second stage multiplies by |1 - 1/s| in double: inside the 1e-5 the
+//    loss terms are held to, with no division per element.  sign(d_j) = -sign(P_j) (s <= 1/2) or +sign(P_j)
+//    (s >= 2) makes the backward division-free too, and its scale gradient closed-form:
+//    sum_j g_d ((P_j / s) / s) = g_abs * sigma * sum |P| / s^2.
+// Scales outside these sets (negative, zero, tiny, huge, NaN, or within a factor 2 of 1 for Difference) and
+// elements that are not ordinary finite numbers take the exact per-element formulation below, as before.
+constexpr float kPenLo = 9.094947017729282e-13f /*2^-40*/, kPenHi = 1099511627776.0f /*2^40*/;
+__host__ __device__ __forceinline__ bool maxbin_fast_scale(float s) { return s >= kPenLo && s <= kPenHi; }
+__host__ __device__ __forceinline__ bool diff_fast_scale(float s) { return (s >= kPenLo && s <= 0.5f) || (s >= 2.0f && s <= kPenHi); }
+
+// MaxBin forward.  fast: acc.c = max |P|.  exact: acc.c = max_j(|P_j| / s), acc.b = how many attain it.
 struct MaxBinStatOp : OpBase<MaxBinStatOp> {
   using Ctx = PenCtx;
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
@@ -25,7 +50,10 @@ struct MaxBinStatOp : OpBase<MaxBinStatOp> {
     if (y.c > x.c) { x.c = y.c; x.b = y.b; }
     else if (y.c == x.c) x.b += y.b;
   }
-  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const { return PenCtx{make_recip(s), aux, 0.f, 0.f, 0.f}; }
+  // k0 = 1: fast regime
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const {
+    return PenCtx{make_recip(s), aux, maxbin_fast_scale(s) ? 1.f : 0.f, 0.f, 0.f};
+  }
   // branch-free (a thread sees only 16 elements per unit, so "is this a new maximum" is true far too
   // often for a branch: the branchy version ran with 24 of 32 lanes live); a NaN quotient is ignored
   // exactly as by the comparisons of combine()
@@ -35,18 +63,21 @@ struct MaxBinStatOp : OpBase<MaxBinStatOp> {
     acc.c = fmaxf(acc.c, d);
   }
   __device__ __forceinline__ void elem(float p, float, const PenCtx& c, const Job&, Acc& acc, float&, float&) const {
+    if (c.k0 != 0.f) { acc.c = fmaxf(acc.c, fabsf(p)); return; }
     take(div_by(fabsf(p), c.rc), acc);                 // LF:92 tf.abs(kernel) / kernel_scale
   }
   __device__ __forceinline__ void quad(const float4& p, const float4&, const PenCtx& c, const Job&, Acc& acc,
                                        float4&, float4&, Defer&) const {
-    float4 d;
-    if (c.rc.fast && fast_range4(p)) {
-      d.x = div_fast(fabsf(p.x), c.rc); d.y = div_fast(fabsf(p.y), c.rc);
-      d.z = div_fast(fabsf(p.z), c.rc); d.w = div_fast(fabsf(p.w), c.rc);
-    } else {
-      d.x = __fdiv_rn(fabsf(p.x), c.rc.s); d.y = __fdiv_rn(fabsf(p.y), c.rc.s);
-      d.z = __fdiv_rn(fabsf(p.z), c.rc.s); d.w = __fdiv_rn(fabsf(p.w), c.rc.s);
+    if (c.k0 != 0.f) {                                  // NaNs drop out of fmaxf as they do out of the comparisons
+      acc.c = fmaxf(fmaxf(acc.c, fabsf(p.x)), fmaxf(fabsf(p.y), fmaxf(fabsf(p.z), fabsf(p.w))));
+      return;
     }
+    exact4(p, c.rc.s, acc);
+  }
+  __device__ __forceinline__ static void exact4(const float4& p, float s, Acc& acc) {
+    float4 d;
+    d.x = __fdiv_rn(fabsf(p.x), s); d.y = __fdiv_rn(fabsf(p.y), s);
+    d.z = __fdiv_rn(fabsf(p.z), s); d.w = __fdiv_rn(fabsf(p.w), s);
     // four at once: the new maximum first, then the ties with it (the count of elements equal to the final
     // maximum does not depend on the order they were seen in); NaNs drop out of fmaxf and of == alike
     const float m4 = fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w));
@@ -58,31 +89,40 @@ struct MaxBinStatOp : OpBase<MaxBinStatOp> {
   }
 };
 
-// Difference forward: sum_j |P_j - P_j / s|  (LF:175-178, un-floored quotient). acc.a = sum.
+// Difference forward: sum_j |P_j - P_j / s|  (LF:175-178, un-floored quotient).
+// fast: acc.a = sum |P| over the ordinary elements; acc.c = exact terms of the others.  exact: acc.c = all terms.
 struct DiffStatOp : OpBase<DiffStatOp> {
   using Ctx = PenCtx;
   static constexpr bool kIn2 = false, kOutIsY = false, kCodes = false, kReduce = true, kAux = false;
   __device__ static void init(Acc& a) { a.a = 0.f; a.b = 0u; a.c = 0.f; }
-  __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
-  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const { return PenCtx{make_recip(s), aux, 0.f, 0.f, 0.f}; }
+  __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; x.c += y.c; }
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job&) const {
+    return PenCtx{make_recip(s), aux, diff_fast_scale(s) ? 1.f : 0.f, 0.f, 0.f};
+  }
+  __device__ __forceinline__ float exact(float p, const PenCtx& c) const { return fabsf(__fsub_rn(p, __fdiv_rn(p, c.rc.s))); }
   __device__ __forceinline__ void elem(float p, float, const PenCtx& c, const Job&, Acc& acc, float&, float&) const {
-    acc.a += fabsf(__fsub_rn(p, div_by(p, c.rc)));
+    const float a = fabsf(p);
+    if (c.k0 != 0.f && a <= kFastHi) acc.a += a; else acc.c += exact(p, c);   // inf / NaN: exact (NaN fails the compare)
   }
   __device__ __forceinline__ void quad(const float4& p, const float4&, const PenCtx& c, const Job&, Acc& acc,
                                        float4&, float4&, Defer&) const {
-    if (c.rc.fast && fast_range4(p)) {
-      acc.a += fabsf(__fsub_rn(p.x, div_fast(p.x, c.rc))); acc.a += fabsf(__fsub_rn(p.y, div_fast(p.y, c.rc)));
-      acc.a += fabsf(__fsub_rn(p.z, div_fast(p.z, c.rc))); acc.a += fabsf(__fsub_rn(p.w, div_fast(p.w, c.rc)));
-    } else {
-      acc.a += fabsf(__fsub_rn(p.x, __fdiv_rn(p.x, c.rc.s))); acc.a += fabsf(__fsub_rn(p.y, __fdiv_rn(p.y, c.rc.s)));
-      acc.a += fabsf(__fsub_rn(p.z, __fdiv_rn(p.z, c.rc.s))); acc.a += fabsf(__fsub_rn(p.w, __fdiv_rn(p.w, c.rc.s)));
-    }
+    const float t = (fabsf(p.x) + fabsf(p.y)) + (fabsf(p.z) + fabsf(p.w));
+    if (c.k0 != 0.f && t <= kFastHi) { acc.a += t; return; }                 // one compare covers inf and NaN
+    acc.c += exact4(p, c.rc.s);
+  }
+  __device__ __forceinline__ static float exact4(const float4& p, float s) {
+    return ((fabsf(__fsub_rn(p.x, __fdiv_rn(p.x, s))) + fabsf(__fsub_rn(p.y, __fdiv_rn(p.y, s)))) +
+            fabsf(__fsub_rn(p.z, __fdiv_rn(p.z, s)))) + fabsf(__fsub_rn(p.w, __fdiv_rn(p.w, s)));
+  }
+  __device__ __forceinline__ Acc warp_reduce(const Acc& x) const {
+    Acc r; r.a = warp_sum(x.a); r.b = 0u; r.c = warp_sum(x.c); return r;
   }
 };
 
-// MaxBin backward w.r.t. P: aux = {mb_g, ties, coef_g = (1/ties) * g_mb}.
+// MaxBin backward w.r.t. P: aux = {mb_g, ties, coef_g = (1/ties) * g_mb, lo_g}.
 //   g_d = indicator(d == mb) * coef ; g_a = g_d / s ; g_P = g_a * sign(P)
 // g_d takes two values per group, so both quotients g_d / s are prepared once: k0 = coef / s, k1 = 0 / s.
+// The indicator is |P| >= lo in the fast regime (lo >= 0) and the quotient comparison otherwise (lo < 0).
 template <bool ACCUM>
 struct MaxBinBwdOp : OpBase<MaxBinBwdOp<ACCUM>> {
   using Ctx = PenCtx;
@@ -94,8 +134,8 @@ struct MaxBinBwdOp : OpBase<MaxBinBwdOp<ACCUM>> {
     return PenCtx{make_recip(s), aux, __fdiv_rn(aux.z, s), __fdiv_rn(0.0f, s), 0.f};
   }
   __device__ __forceinline__ void elem(float p, float old, const PenCtx& c, const Job&, Acc&, float& dx, float&) const {
-    const float d = div_by(fabsf(p), c.rc);
-    const float g = __fmul_rn((d == c.aux.x) ? c.k0 : c.k1, sgn(p));
+    const bool hit = (c.aux.w >= 0.f) ? (fabsf(p) >= c.aux.w) : (div_by(fabsf(p), c.rc) == c.aux.x);
+    const float g = __fmul_rn(hit ? c.k0 : c.k1, sgn(p));
     dx = ACCUM ? __fadd_rn(old, g) : g;
   }
 };
@@ -104,6 +144,8 @@ struct MaxBinBwdOp : OpBase<MaxBinBwdOp<ACCUM>> {
 //   g_P = g_d + (-g_d)/s ;  ds_g += (-g_d) * ((-P / s) / s)
 // With g_abs = t0 * upstream constant per tensor: g_P = sign(d) * (g_abs + (-g_abs)/s) exactly (RN is
 // symmetric under negation), prepared once per group as k1; k0 = g_abs.
+// fast regime (k2 = sigma = -1 / +1): sign(d) = sigma * sign(P), and the scale gradient of the ordinary elements
+// is closed-form from the forward's sum |P| (pen_finalize adds it); only the other elements accumulate here.
 template <bool ACCUM>
 struct DiffBwdOp : OpBase<DiffBwdOp<ACCUM>> {
   using Ctx = PenCtx;
@@ -113,42 +155,247 @@ struct DiffBwdOp : OpBase<DiffBwdOp<ACCUM>> {
   __device__ static void combine(Acc& x, const Acc& y) { x.a += y.a; }
   __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job& j) const {
     const float gabs = __fmul_rn(j.t0, __ldg(up));
-    return PenCtx{make_recip(s), aux, gabs, __fadd_rn(gabs, __fdiv_rn(-gabs, s)), 0.f};
+    const float sigma = diff_fast_scale(s) ? (s <= 0.5f ? -1.f : 1.f) : 0.f;
+    return PenCtx{make_recip(s), aux, gabs, __fadd_rn(gabs, __fdiv_rn(-gabs, s)), sigma};
+  }
+  __device__ __forceinline__ void exact(float p, float old, const PenCtx& c, Acc& acc, float& dx) const {
+    const float pq = __fdiv_rn(p, c.rc.s);
+    const float sg = sgn(__fsub_rn(p, pq));
+    const float g = __fmul_rn(sg, c.k1);
+    acc.a += __fmul_rn(__fmul_rn(-sg, c.k0), __fdiv_rn(-pq, c.rc.s));
+    dx = ACCUM ? __fadd_rn(old, g) : g;
+  }
+  __device__ __forceinline__ void fast1(float p, float old, const PenCtx& c, float& dx) const {
+    const float g = __fmul_rn(__fmul_rn(c.k2, sgn(p)), c.k1);
+    dx = ACCUM ? __fadd_rn(old, g) : g;
   }
   __device__ __forceinline__ void elem(float p, float old, const PenCtx& c, const Job&, Acc& acc, float& dx, float&) const {
-    const float pq = div_by(p, c.rc);
-    const float sg = sgn(__fsub_rn(p, pq));
-    const float g = __fmul_rn(sg, c.k1);
-    acc.a += __fmul_rn(__fmul_rn(-sg, c.k0), div_by(-pq, c.rc));
-    dx = ACCUM ? __fadd_rn(old, g) : g;
+    if (c.k2 != 0.f && fabsf(p) <= kFastHi) fast1(p, old, c, dx); else exact(p, old, c, acc, dx);
   }
-  __device__ __forceinline__ void one_fast(float p, float old, const PenCtx& c, Acc& acc, float& dx) const {
-    const float pq = div_fast(p, c.rc);
-    const float sg = sgn(__fsub_rn(p, pq));
-    acc.a += __fmul_rn(__fmul_rn(-sg, c.k0), div_fast(-pq, c.rc));
-    const float g = __fmul_rn(sg, c.k1);
-    dx = ACCUM ? __fadd_rn(old, g) : g;
-  }
-  __device__ __forceinline__ void quad(const float4& p, const float4& old, const PenCtx& c, const Job& j, Acc& acc,
-                                       float4& dx, float4& q, Defer&) const {
-    // both dividends inside the window: |p| in [2^-80, 2^80] and, with |s| in [2^-40, 2^40], |p / s| in
-    // [2^-120, 2^120] -- the second quotient is checked on its own dividend
-    bool fast = c.rc.fast && fast_range4(p);
-    if (fast) {
-      const float4 pq = make_float4(div_fast(p.x, c.rc), div_fast(p.y, c.rc), div_fast(p.z, c.rc), div_fast(p.w, c.rc));
-      fast = fast_range4(pq);
-    }
-    if (fast) {
-      one_fast(p.x, old.x, c, acc, dx.x); one_fast(p.y, old.y, c, acc, dx.y);
-      one_fast(p.z, old.z, c, acc, dx.z); one_fast(p.w, old.w, c, acc, dx.w);
+  __device__ __forceinline__ void quad(const float4& p, const float4& old, const PenCtx& c, const Job&, Acc& acc,
+                                       float4& dx, float4&, Defer&) const {
+    const float t = (fabsf(p.x) + fabsf(p.y)) + (fabsf(p.z) + fabsf(p.w));     // the forward's split, bit for bit
+    if (c.k2 != 0.f && t <= kFastHi) {
+      fast1(p.x, old.x, c, dx.x); fast1(p.y, old.y, c, dx.y); fast1(p.z, old.z, c, dx.z); fast1(p.w, old.w, c, dx.w);
     } else {
-      elem(p.x, old.x, c, j, acc, dx.x, q.x); elem(p.y, old.y, c, j, acc, dx.y, q.y);
-      elem(p.z, old.z, c, j, acc, dx.z, q.z); elem(p.w, old.w, c, j, acc, dx.w, q.w);
+      exact(p.x, old.x, c, acc, dx.x); exact(p.y, old.y, c, acc, dx.y);
+      exact(p.z, old.z, c, acc, dx.z); exact(p.w, old.w, c, acc, dx.w);
     }
   }
 };
 
 template <class Op> static Op make_pen_op(const float* up) { Op op; op.up = up; return op; }
+
+// --------------------------------------------------------------- lean forward kernels (fast regime)
+// The forward statistics only READ: to run at HBM speed a read-only pass needs about twice the bytes in flight of
+// the read+write kernels, and the generic traversal + operator (four 16-byte loads per lane, 44-64 registers with
+// the exact formulation inlined) sat at 56-71 % DRAM throughput with 42-50 % of the warps resident.  These kernels
+// keep EIGHT 16-byte loads per lane in flight, do one FMNMX (MaxBin) or one FADD (Difference) per element, and hand
+// anything that is not the fast regime -- a scale outside the fast set, unaligned or odd-sized rows, a unit that
+// holds an inf / NaN (Difference) -- to the generic traversal, out of line.  Same geometry, same partials.
+template <int KIND> struct StatKind;
+template <> struct StatKind<LQ_PEN_MAXBIN> { using Op = MaxBinStatOp; };
+template <> struct StatKind<LQ_PEN_DIFFERENCE> { using Op = DiffStatOp; };
+
+template <int KIND>
+__device__ __noinline__ void stat_row_generic(const Job& j, long long unit) {
+  typename StatKind<KIND>::Op op;
+  using IO = LocalIO<false>;
+  if (j.vec) run_row<typename StatKind<KIND>::Op, false, true>(j, 0u, op, nullptr, IO(), unit);
+  else run_row<typename StatKind<KIND>::Op, false, false>(j, 0u, op, nullptr, IO(), unit);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_constant__ JobTable tab) {
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const Job& j = tab.job[lo];
+  const unsigned blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
+  const int lane = threadIdx.x & 31;
+  const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
+  if (unit >= j.units) return;
+  long long row, grp;
+  int sg;
+  if (j.fast32) {
+    const unsigned r = fd_div((unsigned)unit, j.fd_nseg);
+    sg = (int)((unsigned)unit - r * (unsigned)j.nseg);
+    grp = r - fd_div(r, j.fd_C) * (unsigned)j.C;
+    row = r;
+  } else {
+    row = unit / j.nseg;
+    sg = (int)(unit - row * j.nseg);
+    grp = row % j.C;
+  }
+  const float s = __ldg(j.s + grp);
+  const bool fast = (KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s);
+  if (!fast || !j.vec || j.seg > 1024) { stat_row_generic<KIND>(j, unit); return; }      // warp-uniform
+  const long long base = row * j.inner + (long long)sg * j.seg;
+  const long long rem = j.inner - (long long)sg * j.seg;
+  const int nvec = (rem < j.seg ? (int)rem : j.seg) >> 2;                                 // <= 256: one trip
+  const float4* P4 = reinterpret_cast<const float4*>(j.P + base);
+  float4 p[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int v = u * 32 + lane;
+    if (v < nvec) p[u] = j.stream_hint ? __ldcs(P4 + v) : P4[v];
+  }
+  float m = -1.f, a = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if (u * 32 + lane < nvec) {
+      if (KIND == LQ_PEN_MAXBIN) {
+        m = fmaxf(fmaxf(m, fabsf(p[u].x)), fmaxf(fabsf(p[u].y), fmaxf(fabsf(p[u].z), fabsf(p[u].w))));
+      } else {
+        const float t = (fabsf(p[u].x) + fabsf(p[u].y)) + (fabsf(p[u].z) + fabsf(p[u].w));
+        bad |= !(t <= kFastHi);                     // an inf or a NaN among the four
+        a += t;
+      }
+    }
+  }
+  if (KIND == LQ_PEN_DIFFERENCE && __any_sync(0xffffffffu, bad)) { stat_row_generic<KIND>(j, unit); return; }
+  if (KIND == LQ_PEN_MAXBIN) {
+    // m is -1 or >= 0 and never NaN: as signed integers the bit patterns order like the values
+    m = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(m)));
+    if (lane == 0) j.part[unit] = make_float4(0.f, __uint_as_float(0u), m, 0.f);
+  } else {
+    a = warp_sum(a);
+    if (lane == 0) j.part[unit] = make_float4(a, __uint_as_float(0u), 0.f, 0.f);
+  }
+}
+
+template <int KIND>
+__device__ __noinline__ void stat_col_generic(const Job& j, unsigned blk, Acc* smem) {
+  typename StatKind<KIND>::Op op;
+  if (j.vec) run_col<typename StatKind<KIND>::Op, false, true>(j, blk, op, smem, nullptr);
+  else run_col<typename StatKind<KIND>::Op, false, false>(j, blk, op, smem, nullptr);
+}
+
+// COL: a thread owns four adjacent columns (one 16-byte load per row) and walks down its rows, eight rows in flight.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_constant__ JobTable tab) {
+  __shared__ Acc smem[4 * kThreads];
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const Job& j = tab.job[lo];
+  const unsigned blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
+  const long long chunk = blk % j.nchunks;
+  const long long cb = blk / j.nchunks;
+  const int t = threadIdx.x;
+  const int ty = t / j.bx;
+  const int tx = t - ty * j.bx;
+  const long long cv = cb * j.bx + tx;
+  const bool active = (ty < j.by) && (cv < j.ncol);
+  const long long col0 = cv * 4;
+  bool fast = j.vec != 0;
+  if (fast && active) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float s = __ldg(j.s + (col0 + k) / j.inner);
+      fast = fast && ((KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s));
+    }
+  }
+  if (!__syncthreads_and(fast ? 1 : 0)) { stat_col_generic<KIND>(j, blk, smem); return; }   // block-uniform
+  const long long r0 = chunk * j.rpc;
+  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
+  const int rows_mine = active ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
+  const long long stride = (long long)j.by * j.W;
+  const float* Pp = j.P + (active ? (r0 + ty) * j.W + col0 : 0);
+  float v[4];                                       // MaxBin: max |P| ; Difference: sum |P|, per column
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = (KIND == LQ_PEN_MAXBIN) ? -1.f : 0.f;
+  bool bad = false;
+#pragma unroll 1
+  for (int i0 = 0; i0 < rows_blk; i0 += 8) {
+    float4 p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u < rows_mine) p[u] = j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(Pp + u * stride))
+                                                   : *reinterpret_cast<const float4*>(Pp + u * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u < rows_mine) {
+        if (KIND == LQ_PEN_MAXBIN) {
+          v[0] = fmaxf(v[0], fabsf(p[u].x)); v[1] = fmaxf(v[1], fabsf(p[u].y));
+          v[2] = fmaxf(v[2], fabsf(p[u].z)); v[3] = fmaxf(v[3], fabsf(p[u].w));
+        } else {
+          v[0] += fabsf(p[u].x); v[1] += fabsf(p[u].y); v[2] += fabsf(p[u].z); v[3] += fabsf(p[u].w);
+        }
+      }
+    }
+    Pp += 8 * stride;
+  }
+  if (KIND == LQ_PEN_DIFFERENCE) {
+    bad = !(((v[0] + v[1]) + (v[2] + v[3])) <= kFastHi);       // an inf or a NaN anywhere in the thread's columns
+    if (__syncthreads_or(bad ? 1 : 0)) { stat_col_generic<KIND>(j, blk, smem); return; }
+  }
+  // fixed-shape tree over the threads that share a column (same tx, ty = 0..by-1)
+  float* red = reinterpret_cast<float*>(smem);
+  if (j.by > 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[k * kThreads + t] = v[k];
+    int span = 1;
+    while (span < j.by) span <<= 1;
+    for (int st = span >> 1; st >= 1; st >>= 1) {
+      __syncthreads();
+      if (ty < st && ty + st < j.by) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float o = red[k * kThreads + t + st * j.bx];
+          red[k * kThreads + t] = (KIND == LQ_PEN_MAXBIN) ? fmaxf(red[k * kThreads + t], o) : red[k * kThreads + t] + o;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = red[k * kThreads + t];
+  }
+  if (ty == 0 && cv < j.ncol) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      j.part[chunk * j.W + col0 + k] = (KIND == LQ_PEN_MAXBIN) ? make_float4(0.f, __uint_as_float(0u), v[k], 0.f)
+                                                                : make_float4(v[k], __uint_as_float(0u), 0.f, 0.f);
+  }
+}
+
+// Which kernel takes which tensor (measured at 64 Mi): rows of a full 1024-element segment -> the lean ROW kernel
+// (6.5 TB/s); shorter rows -> the generic ROW traversal, whose four loads per lane already cover the whole row (letting
+// a warp take two 512-element rows was slower: 60 us against 47); interleaved layouts -> the lean COL kernel.
+template <int KIND>
+static int launch_stat(JobTable& tab, cudaStream_t st) {
+  JobTable part;
+  for (int cls = 0; cls < 3; ++cls) {              // 0: ROW long rows (lean), 1: ROW short rows (generic), 2: COL (lean)
+    part.n = 0;
+    unsigned total = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      const Job& tj = tab.job[i];
+      if (tj.nblocks == 0) continue;
+      const int c = (tj.regime == REG_COL) ? 2 : ((tj.vec && tj.seg == kSegMax) ? 0 : 1);
+      if (c != cls) continue;
+      part.job[part.n] = tj;
+      part.job[part.n].block_begin = total;
+      total += tj.nblocks;
+      ++part.n;
+    }
+    if (total == 0) continue;
+    int rc;
+    if (cls == 0) rc = launch_after(stat_row_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW launch", part);
+    else if (cls == 2) rc = launch_after(stat_col_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics COL launch", part);
+    else rc = launch_after(mt_kernel<typename StatKind<KIND>::Op, REG_ROW>, dim3(total), dim3(kThreads), st,
+                           "loss-term statistics ROW (short rows) launch", part, typename StatKind<KIND>::Op{});
+    if (rc) return rc;
+  }
+  return LQ_OK;
+}
 
 // --------------------------------------------------------------- second stages
 enum { PFIN_MAXBIN = 1, PFIN_SUM = 2, PFIN_SUM_DS = 3 };
@@ -161,48 +408,141 @@ __global__ void __launch_bounds__(256) pen_fold_kernel(const __grid_constant__ F
   const long long g = blockIdx.x / f.nlin, m = blockIdx.x - g * f.nlin;
   const long long K = partials_per_group(f);
   const long long k0 = m * kFinChunk;
-  double sum = 0.0;
+  const bool sums = f.mode != PFIN_MAXBIN;        // Difference: .x and .z are both sums
+  double sum = 0.0, sum_c = 0.0;
   float mx = -1.f;
   unsigned long long ties = 0ull;
   float4 v[kFinChunk / 256];
 #pragma unroll
   for (int u = 0; u < kFinChunk / 256; ++u) {
     const long long k = k0 + u * 256 + threadIdx.x;
-    v[u] = (k < K) ? f.part[partial_index(f, g, k)] : make_float4(0.f, 0.f, -2.f, 0.f);
+    v[u] = (k < K) ? f.part[partial_index(f, g, k)] : make_float4(0.f, 0.f, sums ? 0.f : -2.f, 0.f);
   }
 #pragma unroll
   for (int u = 0; u < kFinChunk / 256; ++u) {
     sum += (double)v[u].x;
+    if (sums) { sum_c += (double)v[u].z; continue; }
     const unsigned long long b = __float_as_uint(v[u].y);
     if (v[u].z > mx) { mx = v[u].z; ties = b; } else if (v[u].z == mx) ties += b;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sum_c += __shfl_xor_sync(0xffffffffu, sum_c, o);
     const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
     const unsigned long long ot = __shfl_xor_sync(0xffffffffu, ties, o);
     if (omx > mx) { mx = omx; ties = ot; } else if (omx == mx) ties += ot;
   }
-  __shared__ double ssum[8];
+  __shared__ double ssum[8], ssumc[8];
   __shared__ unsigned long long sties[8];
   __shared__ float smx[8];
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; sties[w] = ties; smx[w] = mx; }
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; ssumc[w] = sum_c; sties[w] = ties; smx[w] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    sum = ssum[0]; ties = sties[0]; mx = smx[0];
+    sum = ssum[0]; sum_c = ssumc[0]; ties = sties[0]; mx = smx[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
-      sum += ssum[i];
+      sum += ssum[i]; sum_c += ssumc[i];
       if (smx[i] > mx) { mx = smx[i]; ties = sties[i]; } else if (smx[i] == mx) ties += sties[i];
     }
-    f.lin[blockIdx.x] = make_float4((float)sum, __uint_as_float((unsigned)(ties > 0xffffffffull ? 0xffffffffull : ties)), mx, 0.f);
+    f.lin[blockIdx.x] = make_float4((float)sum, __uint_as_float((unsigned)(ties > 0xffffffffull ? 0xffffffffull : ties)),
+                                    sums ? (float)sum_c : mx, 0.f);
   }
+}
+
+// MaxBin, fast regime: the block that has just reduced group g counts the elements whose quotient equals the
+// group's maximum.  Only first-level partials (a ROW unit, or one column of a COL row chunk) whose own max |P|
+// reaches lo can hold such elements -- normally one per group: they are collected in a small shared list and
+// re-read by the whole block.  Integer counts: the result does not depend on any order.  Groups whose candidates
+// do not fit the list, and large groups that must compare quotients (lo = -2), are left to pen_ties_kernel.
+constexpr int kTieList = 256;
+
+__device__ __forceinline__ long long partial_index1(const FinJob& f, long long g, long long k) {
+  if (f.regime1 == REG_ROW) {
+    const long long o = k / f.nseg, sg = k - o * f.nseg;
+    return (o * f.C + g) * f.nseg + sg;
+  }
+  const long long ch = k / f.inner, ci = k - ch * f.inner;
+  return ch * f.W + g * f.inner + ci;
+}
+
+__device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb) {
+  __shared__ long long list[kTieList];
+  __shared__ int nlist, nlin_list;
+  __shared__ unsigned total;
+  __shared__ long long lin_list[32];
+  const long long K1 = (f.regime1 == REG_ROW) ? f.outer * f.nseg : f.nchunks * f.inner;   // first-level partials of the group
+  const bool all = lo == -2.f;
+  if (threadIdx.x == 0) { nlist = 0; nlin_list = 0; total = 0u; }
+  __syncthreads();
+  bool overflow = all && K1 > kTieList;
+  if (!overflow) {
+    if (f.regime == REG_LIN) {
+      // two levels: the intermediate partials that reach lo first, then the first-level partials behind them
+      for (long long k = threadIdx.x; k < f.nlin; k += kFinThreads)
+        if (all || f.part[g * f.nlin + k].z >= lo) { const int i = atomicAdd(&nlin_list, 1); if (i < 32) lin_list[i] = k; }
+      __syncthreads();
+      const int nl = nlin_list;
+      if (nl > 32) overflow = true;
+      for (int i = 0; i < nl && !overflow; ++i) {
+        const long long k0 = lin_list[i] * kFinChunk;
+        for (long long k = k0 + threadIdx.x; k < k0 + kFinChunk && k < K1; k += kFinThreads)
+          if (all || f.part1[partial_index1(f, g, k)].z >= lo) { const int n = atomicAdd(&nlist, 1); if (n < kTieList) list[n] = k; }
+      }
+    } else {
+      // same walk as the reduction above (four loads in flight; no index arithmetic where partials sit at a stride)
+      const bool simple = (f.regime1 == REG_ROW && f.nseg == 1) || (f.regime1 == REG_COL && f.inner == 1);
+      const long long stride = (f.regime1 == REG_ROW) ? f.C : f.W;
+      for (long long k0 = threadIdx.x; k0 < K1; k0 += 4 * kFinThreads) {
+        float z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long k = k0 + (long long)u * kFinThreads;
+          z[u] = (k < K1) ? (simple ? f.part1[g + k * stride].z : f.part1[partial_index1(f, g, k)].z) : -1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long k = k0 + (long long)u * kFinThreads;
+          if (k < K1 && (all || z[u] >= lo)) { const int n = atomicAdd(&nlist, 1); if (n < kTieList) list[n] = k; }
+        }
+      }
+    }
+    __syncthreads();
+    if (nlist > kTieList) overflow = true;
+  }
+  if (overflow) {                               // block-uniform: mark the group pending (.z = 1) for pen_ties_kernel
+    if (threadIdx.x == 0) f.gstat[g].z = 1.f;
+    return;
+  }
+  const float sc = all ? f.s[g] : 1.f;
+  unsigned cnt = 0;
+  const int n = nlist;
+  for (int i = 0; i < n; ++i) {
+    const long long k = list[i];
+    if (f.regime1 == REG_ROW) {
+      const long long o = k / f.nseg, sg = k - o * f.nseg;
+      const long long base = (o * f.C + g) * f.inner + sg * f.seg;
+      const long long rem = f.inner - sg * f.seg;
+      const int len = rem < f.seg ? (int)rem : f.seg;
+      for (int e = threadIdx.x; e < len; e += kFinThreads) cnt += tie_hit(f.P[base + e], lo, mb, sc);
+    } else {
+      const long long ch = k / f.inner, ci = k - ch * f.inner;
+      const long long col = g * f.inner + ci;
+      const long long r0 = ch * f.rpc;
+      const long long r1 = (r0 + f.rpc < f.outer) ? r0 + f.rpc : f.outer;
+      for (long long r = r0 + threadIdx.x; r < r1; r += kFinThreads) cnt += tie_hit(f.P[r * f.W + col], lo, mb, sc);
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) f.gstat[g].y = __uint_as_float(total);
 }
 
 __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g) {
   const long long K = partials_per_group(f);
-  double sum = 0.0;
+  double sum = 0.0, sum_c = 0.0;
   float mx = -1.f;
   unsigned long long ties = 0ull;
   // four independent 16-byte loads per thread per trip, and no 64-bit division on the layouts whose
@@ -211,16 +551,18 @@ __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g)
   const bool simple = (f.regime == REG_ROW && f.nseg == 1) || f.regime == REG_LIN || (f.regime == REG_COL && f.inner == 1);
   const long long stride = (f.regime == REG_ROW) ? f.C : (f.regime == REG_COL ? f.W : 1);
   const float4* base = f.part + ((f.regime == REG_LIN) ? g * f.nlin : g);
+  const bool sums = f.mode != PFIN_MAXBIN;
   for (long long k0 = threadIdx.x; k0 < K; k0 += 4 * kFinThreads) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long k = k0 + (long long)u * kFinThreads;
-      v[u] = (k < K) ? (simple ? base[k * stride] : f.part[partial_index(f, g, k)]) : make_float4(0.f, 0.f, -2.f, 0.f);
+      v[u] = (k < K) ? (simple ? base[k * stride] : f.part[partial_index(f, g, k)]) : make_float4(0.f, 0.f, sums ? 0.f : -2.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       sum += (double)v[u].x;
+      if (sums) { sum_c += (double)v[u].z; continue; }      // Difference: .z is the sum of the exactly evaluated terms
       const unsigned long long b = __float_as_uint(v[u].y);
       if (v[u].z > mx) { mx = v[u].z; ties = b; } else if (v[u].z == mx) ties += b;
     }
@@ -228,33 +570,76 @@ __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sum_c += __shfl_xor_sync(0xffffffffu, sum_c, o);
     const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
     const unsigned long long ot = __shfl_xor_sync(0xffffffffu, ties, o);
     if (omx > mx) { mx = omx; ties = ot; } else if (omx == mx) ties += ot;
   }
-  __shared__ double ssum[kFinThreads / 32];
+  __shared__ double ssum[kFinThreads / 32], ssumc[kFinThreads / 32];
   __shared__ unsigned long long sties[kFinThreads / 32];
   __shared__ float smx[kFinThreads / 32];
+  __shared__ float tie_lo, tie_mb;            // MaxBin fast regime: what the block counts after the reduction
+  if (threadIdx.x == 0) tie_lo = -1.f;
   const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; sties[w] = ties; smx[w] = mx; }
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; ssumc[w] = sum_c; sties[w] = ties; smx[w] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    sum = ssum[0]; ties = sties[0]; mx = smx[0];
+    sum = ssum[0]; sum_c = ssumc[0]; ties = sties[0]; mx = smx[0];
 #pragma unroll
     for (int i = 1; i < kFinThreads / 32; ++i) {
-      sum += ssum[i];
+      sum += ssum[i]; sum_c += ssumc[i];
       if (smx[i] > mx) { mx = smx[i]; ties = sties[i]; } else if (smx[i] == mx) ties += sties[i];
     }
+    const float sc = f.s[g];
     if (f.mode == PFIN_MAXBIN) {
-      f.gstat[g] = make_float4(mx, __uint_as_float((unsigned)(ties > 0xffffffffull ? 0xffffffffull : ties)), 0.f, 0.f);
+      const unsigned t32 = (unsigned)(ties > 0xffffffffull ? 0xffffffffull : ties);
+      if (!maxbin_fast_scale(sc) || mx < 0.f) {
+        // exact regime (mx is the largest quotient, ties counted by the element pass), or nothing but NaNs
+        f.gstat[g] = make_float4(mx, __uint_as_float(t32), 0.f, -1.f);
+      } else {
+        // fast regime: mx is max |P| and the maximum is RN(max |P| / s) (division by s > 0 is monotone): ONE
+        // division per group.  The tied elements are those with |P| >= lo, lo = the smallest float whose quotient
+        // still rounds to the maximum (a handful of ulps below mx at most); when max |P| is zero, denormal-small,
+        // huge or infinite they are found by comparing quotients instead (lo = -2).  Counted below by the block.
+        const float mb = __fdiv_rn(mx, sc);
+        float lo = -2.f;
+        if (mx >= kFastLo && mx <= kFastHi) {
+          lo = mx;
+          for (int i = 0; i < 16; ++i) {
+            const float a = __uint_as_float(__float_as_uint(lo) - 1u);
+            if (__fdiv_rn(a, sc) != mb) break;
+            lo = a;
+          }
+        }
+        tie_lo = lo; tie_mb = mb;
+        f.gstat[g] = make_float4(mb, __uint_as_float(0u), 0.f, lo);
+      }
     } else if (f.mode == PFIN_SUM) {
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(sum);
-      f.gstat[g] = make_float4(__uint_as_float((unsigned)(bits & 0xffffffffull)), __uint_as_float((unsigned)(bits >> 32)), 0.f, 0.f);
-    } else {   // PFIN_SUM_DS
-      const float v = (float)sum;
-      f.ds[g] = (f.flags & LQ_F_ACCUM_DS) ? __fadd_rn(f.ds[g], v) : v;
+      // Difference: fast part sum |P| * |1 - 1/s| (double) + the exactly evaluated terms
+      const double k = diff_fast_scale(sc) ? fabs(1.0 - 1.0 / (double)sc) : 0.0;
+      const double val = sum * k + sum_c;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+      const unsigned long long abits = (unsigned long long)__double_as_longlong(sum);
+      f.gstat[g] = make_float4(__uint_as_float((unsigned)(bits & 0xffffffffull)), __uint_as_float((unsigned)(bits >> 32)),
+                               __uint_as_float((unsigned)(abits & 0xffffffffull)), __uint_as_float((unsigned)(abits >> 32)));
+    } else {   // PFIN_SUM_DS: exactly evaluated terms + the closed form of the fast part (see DiffBwdOp)
+      double v = sum;
+      if (diff_fast_scale(sc)) {
+        const float4 st = f.gstat[g];
+        const unsigned long long abits = (unsigned long long)__float_as_uint(st.z) | ((unsigned long long)__float_as_uint(st.w) << 32);
+        const double S = __longlong_as_double((long long)abits);
+        const double gabs = (double)__fmul_rn(f.p0, *f.up);
+        v += gabs * (sc <= 0.5f ? -1.0 : 1.0) * S / ((double)sc * (double)sc);
+      }
+      const float r = (float)v;
+      f.ds[g] = (f.flags & LQ_F_ACCUM_DS) ? __fadd_rn(f.ds[g], r) : r;
     }
   }
+  if (f.mode != PFIN_MAXBIN) return;
+  __syncthreads();
+  const float lo = tie_lo, mb = tie_mb;
+  if (lo == -1.f) return;                      // exact regime / nothing but NaNs: already final
+  pen_count_ties(f, g, lo, mb);
 }
 
 __global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_constant__ FinTable tab) {
@@ -266,6 +651,61 @@ __global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_
   const FinJob& f = tab.job[lo];
   cudaGridDependencySynchronize();
   pen_finalize_group(f, blockIdx.x - f.group_begin);
+}
+
+// The groups pen_count_ties left pending (gstat.z == 1: more candidate units than its list holds -- many equal
+// maxima -- or a large group that must compare quotients, gstat.w == -2): thread <-> first-level partial, a warp
+// re-reads the flagged ones.  Rare by construction; a fixed small grid walks all partials.
+struct TieTable { int n; unsigned begin[kMaxMT]; };
+constexpr unsigned kTieBlocksPerTensor = 64;
+
+__global__ void __launch_bounds__(256) pen_ties_kernel(const __grid_constant__ JobTable tab, const __grid_constant__ TieTable tt) {
+  int lo_i = 0, hi_i = tt.n - 1;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (tt.begin[mid] <= blockIdx.x) lo_i = mid; else hi_i = mid - 1;
+  }
+  const Job& j = tab.job[lo_i];
+  cudaGridDependencySynchronize();
+  float4* gstat = const_cast<float4*>(j.gaux);
+  const long long npart = (j.regime == REG_ROW) ? j.units : j.nchunks * j.W;
+  const unsigned nblk = ((lo_i + 1 < tt.n) ? tt.begin[lo_i + 1] : gridDim.x) - tt.begin[lo_i];
+  const int lane = threadIdx.x & 31;
+  for (long long s0 = (long long)(blockIdx.x - tt.begin[lo_i]) * 256; s0 < npart; s0 += 256ll * nblk) {
+    const long long slot = s0 + threadIdx.x;
+    long long a = 0, b = 0, grp = 0;      // ROW: a = row, b = segment;  COL: a = chunk, b = column
+    float lo = -1.f, mb = 0.f;
+    bool flagged = false;
+    if (slot < npart) {
+      if (j.regime == REG_ROW) { a = slot / j.nseg; b = slot - a * j.nseg; grp = a % j.C; }
+      else { a = slot / j.W; b = slot - a * j.W; grp = b / j.inner; }
+      const float4 st = gstat[grp];
+      lo = st.w; mb = st.x;
+      flagged = st.z == 1.f && (lo == -2.f || j.part[slot].z >= lo);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, flagged);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const long long ua = __shfl_sync(0xffffffffu, a, src), ub = __shfl_sync(0xffffffffu, b, src);
+      const long long ug = __shfl_sync(0xffffffffu, grp, src);
+      const float ulo = __shfl_sync(0xffffffffu, lo, src), umb = __shfl_sync(0xffffffffu, mb, src);
+      const float sc = (ulo == -2.f) ? __ldg(j.s + ug) : 1.f;
+      unsigned cnt = 0;
+      if (j.regime == REG_ROW) {
+        const long long base = ua * j.inner + ub * j.seg;
+        const long long rem = j.inner - ub * j.seg;
+        const int len = rem < j.seg ? (int)rem : j.seg;
+        for (int e = lane; e < len; e += 32) cnt += tie_hit(j.P[base + e], ulo, umb, sc);
+      } else {
+        const long long r0 = ua * j.rpc;
+        const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+        for (long long r = r0 + lane; r < r1; r += 32) cnt += tie_hit(j.P[r * j.W + ub], ulo, umb, sc);
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned*>(&gstat[ug].y), cnt);
+    }
+  }
 }
 
 // Per-tensor scalar stage: penalty = sum_t mean_t * dim_t / normalizer (LF:110-116 etc.)
@@ -367,6 +807,32 @@ static int pen_fold_large(FinTable& fin, cudaStream_t st) {
   return LQ_OK;
 }
 
+// Geometry of the forward statistics on interleaved layouts: narrow column blocks (a warp reads 512 contiguous bytes
+// per row), eight threads deep, LONG row chunks -- the second stage walks chunks-per-group partials, and with the
+// element kernels' 64-row chunks a [131072, 512] tensor had 2048 of them per group (25 us of second stage for a
+// 45 us pass).  Never more partials than the default geometry the workspace is sized for.
+static Geom make_stat_geom(long long outer, long long C, long long inner, bool aligned) {
+  Geom g = make_geom(outer, C, inner, aligned);
+  if (g.regime != REG_COL || !g.vec_ok) return g;
+  const int bx = g.ncol < 32 ? (int)g.ncol : 32;
+  const int by = kThreads / bx;
+  const long long ncolblk = cdiv(g.ncol, bx);
+  long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * 8), by) * by;
+  if (rpc < by) rpc = by;
+  if (rpc > 1024) rpc = 1024 / by * by;
+  if (rpc > outer) rpc = outer;
+  if (rpc <= g.rpc) return g;                       // short tensors: the default chunks are already the longer ones
+  g.bx = bx; g.by = by; g.rpc = (int)rpc;
+  g.nchunks = cdiv(outer, rpc);
+  g.ncolblk = ncolblk;
+  g.nblocks = g.nchunks * ncolblk;
+  g.npart1 = g.nchunks * g.W;
+  g.kper = g.nchunks * inner;
+  g.nlin = g.kper > kFinSplit ? cdiv(g.kper, kFinChunk) : 0;
+  g.npartials = g.npart1 + C * g.nlin;
+  return g;
+}
+
 struct PenLayout { size_t part_off, gstat_off; };
 
 static size_t pen_slots(const lq_tensor_desc& d) {
@@ -428,8 +894,8 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
   double* total = reinterpret_cast<double*>(base + soff);
   for (int i0 = 0; i0 < n && !rc; i0 += kMaxMT) {
     const int i1 = (i0 + kMaxMT < n) ? i0 + kMaxMT : n;
-    JobTable tab{}; FinTable fin{}; ScalarTable sc{};
-    unsigned groups = 0;
+    JobTable tab{}; FinTable fin{}; ScalarTable sc{}; TieTable ties{};
+    unsigned groups = 0, tie_blocks = 0;
     sc.kind = kind; sc.first = (i0 == 0); sc.last = (i1 == n); sc.normalizer = nrm;
     for (int i = i0; i < i1; ++i) {
       const lq_tensor_desc& d = descs[i];
@@ -438,14 +904,21 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
       float4* part = reinterpret_cast<float4*>(base + lay[i].part_off);
       float4* gstat = reinterpret_cast<float4*>(base + lay[i].gstat_off);
       if (kind != LQ_PEN_INVERSE) {
-        Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P));
+        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P));
         if (g.nblocks > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
         Job j = make_job(g, d.P, d.s, nullptr, nullptr, nullptr, nullptr, 0, part);
+        j.gaux = gstat;                                           // pen_ties_kernel: the group's {max, ties, -, lo}
         tab.job[tab.n++] = j;
+        long long nb = cdiv(g.npart1, 256);
+        if (nb > kTieBlocksPerTensor) nb = kTieBlocksPerTensor;
+        if ((long long)tie_blocks + nb > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
+        ties.begin[ties.n++] = tie_blocks;
+        tie_blocks += (unsigned)nb;
         FinJob f{};
         f.part = part; f.gstat = gstat; f.s = d.s; f.ds = nullptr;
         f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
         f.regime = g.regime; f.mode = (kind == LQ_PEN_MAXBIN) ? PFIN_MAXBIN : PFIN_SUM;
+        f.P = d.P; f.part1 = part; f.regime1 = g.regime; f.seg = g.seg; f.rpc = g.rpc;
         f.nlin = g.nlin; f.lin = part + g.npart1;
         f.group_begin = groups; groups += (unsigned)d.C;
         fin.job[fin.n++] = f;
@@ -454,11 +927,13 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
     }
     if (rc) break;
     if (tab.n) {
-      if (kind == LQ_PEN_MAXBIN) rc = launch_mt(tab, MaxBinStatOp{}, st);
-      else rc = launch_mt(tab, DiffStatOp{}, st);
+      if (kind == LQ_PEN_MAXBIN) rc = launch_stat<LQ_PEN_MAXBIN>(tab, st);
+      else rc = launch_stat<LQ_PEN_DIFFERENCE>(tab, st);
       if (rc) break;
       if ((rc = pen_fold_large(fin, st))) break;
       if ((rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty finalize launch", fin))) break;
+      if (kind == LQ_PEN_MAXBIN && tie_blocks &&
+          (rc = launch_after(pen_ties_kernel, dim3(tie_blocks), dim3(256), st, "penalty tie launch", tab, ties))) break;
     }
     rc = launch_after(pen_scalar_kernel, dim3(1), dim3(256), st, "penalty scalar launch", sc, total, out_penalty);
   }
@@ -518,6 +993,7 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
           f.part = part; f.gstat = gstat; f.s = d.s; f.ds = d.ds;
           f.C = g.C; f.inner = g.inner; f.W = g.W; f.outer = g.outer; f.nseg = g.nseg; f.nchunks = g.nchunks;
           f.regime = g.regime; f.mode = PFIN_SUM_DS; f.flags = d.flags;
+          f.p0 = j.t0; f.up = up;                                  // the closed-form part needs g_abs = t0 * upstream
           f.nlin = g.nlin; f.lin = part + g.npart1;
           f.group_begin = groups;
           fin.job[fin.n++] = f;

@@ -95,11 +95,26 @@ struct LocalIO {
   __device__ __forceinline__ void st_part(float4* p, const float4& v) const { *p = v; }
 };
 
+#ifndef LQ_STAT_UNROLL
+#define LQ_STAT_UNROLL 4
+#endif
+#ifndef LQ_STAT_MINBLK
+#define LQ_STAT_MINBLK 8
+#endif
+// resident blocks per SM asked of the compiler for the ROW multi-tensor kernel: the read-only reductions are
+// latency-bound (more warps in flight = more bytes in flight), everything else keeps its registers
+template <class Op>
+constexpr int kRowMinBlocks = (!Op::kIn2 && Op::kReduce && !Op::kOutIsY) ? LQ_STAT_MINBLK : 1;
+
+template <class Op>
+struct RowUnroll { static constexpr int value = (!Op::kIn2 && Op::kReduce && !Op::kOutIsY) ? LQ_STAT_UNROLL : 4; };
+
 // ------------------------------------------------------------------------- ROW regime
 template <class Op, bool STREAM, bool VEC, class IO = LocalIO<STREAM>>
-__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op, float2* queue, const IO& io = IO()) {
+__device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op, float2* queue, const IO& io = IO(),
+                                        long long unit_override = -1) {
   const int lane = threadIdx.x & 31;
-  const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
+  const long long unit = unit_override >= 0 ? unit_override : (long long)blk * kWarps + (threadIdx.x >> 5);
   if (unit >= j.units) return;
   long long row, grp;
   int sg;
@@ -131,22 +146,25 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
     const float4* P4 = reinterpret_cast<const float4*>(j.P + base);
     const float4* D4 = reinterpret_cast<const float4*>(j.dy + base);
     float4* O4 = reinterpret_cast<float4*>(out + base);
-    for (int v0 = 0; v0 < nvec; v0 += 128) {
-      float4 p[4], d[4];
+    // loads in flight per lane and trip: 4 x 16 B per array (8 was measured for the read-only reductions:
+    // 73 registers, 31 % warps active, slower)
+    constexpr int UR = RowUnroll<Op>::value;
+    for (int v0 = 0; v0 < nvec; v0 += 32 * UR) {
+      float4 p[UR], d[Op::kIn2 ? UR : 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UR; ++u) {
         const int v = v0 + u * 32 + lane;
         if (v < nvec) {
           p[u] = ld4<STREAM>(P4 + v);
-          if (Op::kIn2) d[u] = io.ld_in2_4(D4 + v);
+          if (Op::kIn2) d[Op::kIn2 ? u : 0] = io.ld_in2_4(D4 + v);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UR; ++u) {
         const int v = v0 + u * 32 + lane;
         if (v < nvec) {
           float4 o, c;
-          op.quad(p[u], Op::kIn2 ? d[u] : make_float4(0.f, 0.f, 0.f, 0.f), ctx, j, acc, o, c, df);
+          op.quad(p[u], Op::kIn2 ? d[Op::kIn2 ? u : 0] : make_float4(0.f, 0.f, 0.f, 0.f), ctx, j, acc, o, c, df);
           if (wr) io.st_out4(O4 + v, o);
           if (Op::kCodes && j.codes) {
             const long long e = base + 4ll * v;
@@ -475,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, kColMinBlocks<Op>) col_kernel(const 
 // regime (a launch holds the ROW tensors or the COL tensors of a step, never both), so that the ROW
 // units keep the ROW kernel's register budget: the combined kernel needed 114 registers.
 template <class Op, int REGIME>
-__global__ void __launch_bounds__(kThreads, REGIME == REG_COL ? kColMinBlocks<Op> : 1) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
+__global__ void __launch_bounds__(kThreads, REGIME == REG_COL ? kColMinBlocks<Op> : kRowMinBlocks<Op>) mt_kernel(const __grid_constant__ JobTable tab, const Op op) {
   __shared__ Acc smem[REGIME == REG_COL ? SmemPlan<Op>::kColEntries : 1];
   __shared__ float2 queue[SmemPlan<Op>::kQueueEntries];
   int lo = 0, hi = tab.n - 1;

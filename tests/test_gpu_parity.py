@@ -567,6 +567,59 @@ def test_maxbin_ties_inside_and_across_quads(lq, shape, s_shape):
         assert float(np.max(np.abs(got - want))) <= TOL * max(float(np.max(np.abs(want))), 1e-30)
 
 
+@pytest.mark.parametrize("shape,s_shape", [((64, 8, 256), (1, 8, 1)), ((4096, 24), (1, 24)), ((1 << 21,), (1,)),
+                                           ((40, 3, 2000), (1, 3, 1))])
+@pytest.mark.parametrize("fill", ["constant", "zeros", "one_ulp_below", "tiny", "mixed_scales"])
+def test_maxbin_tie_counting_corner_cases(lq, shape, s_shape, fill):
+    """The MaxBin passes work on |P| and divide once per group; ties in the QUOTIENT are what TF's reduce_max
+    gradient splits over (LF:90-94).  Cases the |P|-domain shortcut must get right: every element tied (more
+    candidate units than the second stage's list holds), all-zero groups, elements one ulp below the maximum
+    whose quotient still rounds to it, values below the fast window, and scales outside the fast set."""
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(17)
+    K = rng.normal(0, 0.05, size=shape).astype(np.float32)
+    sK = rng.uniform(5e-3, 2e-2, size=s_shape).astype(np.float32)
+    if fill == "constant":
+        K[...] = np.float32(0.25) * np.where(rng.random(shape) < 0.5, -1, 1).astype(np.float32)
+    elif fill == "zeros":
+        K[...] = 0.0
+        K.reshape(-1)[::7] = -0.0
+    elif fill == "one_ulp_below":
+        top = np.float32(0.8125)
+        flat = K.reshape(-1)
+        idx = rng.choice(flat.size, size=min(flat.size // 3, 5000), replace=False)
+        flat[idx[0::3]] = top
+        flat[idx[1::3]] = np.nextafter(top, np.float32(0))
+        flat[idx[2::3]] = -np.nextafter(np.nextafter(top, np.float32(0)), np.float32(0))
+    elif fill == "tiny":
+        K *= np.float32(1e-30)
+    else:
+        sK.reshape(-1)[0] = np.float32(1e-14)          # below the fast window: exact regime for that group
+        if sK.size > 1:
+            sK.reshape(-1)[1] = np.float32(3e13)
+    b = np.array([0.3, -0.3, 0.3, 0.1], np.float32)
+    sb = np.array([0.01], np.float32)
+    layers = [(K, sK, b, sb)]
+    Ps, ss = [dev(K), dev(b)], [dev(sK), dev(sb)]
+    out, ws = ops.penalty_fwd(_lib.LQ_PEN_MAXBIN, Ps, ss)
+    assert rel_err(host(out), o.maxbin_penalty(layers)) < TOL
+    dXs, dss = ops.penalty_bwd(_lib.LQ_PEN_MAXBIN, Ps, ss, ws, 1.0)
+    (gK, gsK, gb, gsb), = o.maxbin_penalty_grads(layers, 1.0, accum="fp64")
+    for got, want in ((dXs[0], gK), (dXs[1], gb), (dss[0], gsK), (dss[1], gsb)):
+        got = host(got).astype(np.float64).reshape(want.shape)
+        assert np.array_equal(got != 0, want != 0)                 # exactly the tied elements carry gradient
+        assert float(np.max(np.abs(got - want))) <= TOL * max(float(np.max(np.abs(want))), 1e-30)
+    # Difference on the same tensors (fast and exact regimes side by side for "mixed_scales")
+    out, ws = ops.penalty_fwd(_lib.LQ_PEN_DIFFERENCE, Ps, ss)
+    assert rel_err(host(out), o.difference_penalty(layers)) < TOL
+    dXs, dss = ops.penalty_bwd(_lib.LQ_PEN_DIFFERENCE, Ps, ss, ws, 1.0)
+    (gK, gsK, gb, gsb), = o.difference_penalty_grads(layers, 1.0, accum="fp64")
+    for got, want in ((dXs[0], gK), (dXs[1], gb), (dss[0], gsK), (dss[1], gsb)):
+        got = host(got).astype(np.float64).reshape(want.shape)
+        assert float(np.max(np.abs(got - want))) <= TOL * max(float(np.max(np.abs(want))), 1e-30)
+
+
 def test_penalties_many_tensors_and_a_huge_group(lq):
     """More tensors than one kernel-parameter table holds (the scalar stage chains over launches) and a
     per-tensor scale on a 9.4 M-element kernel (more than 4096 partials: the two-level fold)."""

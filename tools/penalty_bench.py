@@ -39,15 +39,19 @@ def main():
              "micro_64Mi_per_tensor": [((1 << 26,), (1,))],
              "micro_64Mi_interleaved": [((131072, 512), (1, 512))]}
     import tools.mt_bench as mb  # noqa: E402
+    quick = os.environ.get("PEN_QUICK")          # A/B runs: the three 64 Mi layouts, forward passes of MaxBin / Difference
     cases["imagenette_inventory"] = [(k, ops.scale_shape(k, "channelwise")) for k in mb.KERNELS] + \
                                     [((k[-1],), (1,)) for k in mb.KERNELS]
+    if quick:
+        cases.pop("imagenette_inventory")
     for name, shapes in cases.items():
         Ps = [torch.empty(s, device="cuda").normal_(0, 0.05, generator=g) for s, _ in shapes]
         ss = [torch.empty(t, device="cuda").uniform_(5e-3, 2e-2, generator=g) for _, t in shapes]
         n = sum(p.numel() for p in Ps)
         dXs = [torch.empty_like(p) for p in Ps]
         dss = [torch.empty_like(s) for s in ss]
-        for kname, kind in (("maxbin", _lib.LQ_PEN_MAXBIN), ("difference", _lib.LQ_PEN_DIFFERENCE), ("inverse", _lib.LQ_PEN_INVERSE)):
+        kinds = (("maxbin", _lib.LQ_PEN_MAXBIN), ("difference", _lib.LQ_PEN_DIFFERENCE), ("inverse", _lib.LQ_PEN_INVERSE))
+        for kname, kind in (kinds[:2] if quick else kinds):
             out, ws = ops.penalty_fwd(kind, Ps, ss)
             f_us = timed(lambda: ops.penalty_fwd(kind, Ps, ss))
             b_us = timed(lambda: ops.penalty_bwd(kind, Ps, ss, ws, 1.0, dXs=dXs, dss=dss))

@@ -1,6 +1,5 @@
 #!/bin/bash
-# same box: the single-GPU QAT step, then the N-GPU step with the exchange variants (bench.py --only-qat)
-N=${1:-2}
+N=${1:-8}
 show() { python -c "
 import json,sys
 for l in sys.stdin:
@@ -12,7 +11,6 @@ one
 run --qat-skip-exchange
 run
 run --qat-no-overlap
-one
-run --qat-skip-exchange
-run
 run --qat-comm nccl
+run --qat-late-blocks 16
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/dpx_probe.py 2>/dev/null | grep floats
