@@ -88,6 +88,16 @@ int lq_fq_fwd(const float* P, const float* s, float* y, void* codes, int codes_d
               int64_t outer, int64_t C, int64_t inner, int round_mode, float qmin, float qmax,
               lq_stream_t stream);
 
+/* a1 with the per-group statistics the loss terms and the callbacks are functions of, as by-products of the same
+ * HBM pass (no second read of P):  stats[3g .. 3g+2] = { min P, max P, sum |P - P / s| } over group g.
+ *   max |q| of the group (custom_callbacks.py:84-129) = max(|floor(min P / s)|, |floor(max P / s)|);
+ *   MaxBin's per-group term (LF:90-94) = max(|min P|, |max P|) / s   (division by s > 0 is monotone);
+ *   Difference's per-group sum (LF:175-178) = stats[3g+2].
+ * NaN elements drop out of the extremes and poison the sum.  ws >= lq_workspace_bytes(.., LQ_PHASE_BWD). */
+int lq_fq_fwd_stats(const float* P, const float* s, float* y, void* codes, int codes_dtype,
+                    int64_t outer, int64_t C, int64_t inner, int round_mode, float qmin, float qmax,
+                    float* stats, void* ws, size_t ws_bytes, lq_stream_t stream);
+
 /* a2 backward, NQ:62-118:  dX = dy (skipped when dX is NULL or == dy) and
  * ds[g] = mean_g(e) * max_g|q|, e as in NQ:103-111, recomputing q,y from P,s in registers.
  * One HBM pass + a deterministic second-stage reduce over block partials in `ws`. */

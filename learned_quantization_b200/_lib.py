@@ -55,6 +55,7 @@ SIGNATURES = {
     "lq_device_sm_count": (_I, []),
     "lq_workspace_bytes": (_I, [_DESCS, _I, _I, C.POINTER(_SZ)]),
     "lq_fq_fwd": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _F, _F, _P]),
+    "lq_fq_fwd_stats": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _I64, _I, _F, _F, _P, _P, _SZ, _P]),
     "lq_fq_bwd_threshold": (_I, [_P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _SZ, _P]),
     "lq_fq_bwd_threshold_stats": (_I, [_P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _SZ, _P]),
     "lq_fq_bwd_threshold_finish": (_I, [_P, _I, _I64, _F, C.c_double, _P, _P]),

@@ -34,6 +34,69 @@ struct FwdOp : OpBase<FwdOp<EXT>> {
   }
 };
 
+// K1 with the per-group statistics of SURVEY 8b as by-products of the same pass: min P, max P (what the callbacks'
+// max |q| and the MaxBin term are functions of: floor and division by s > 0 are monotone) and sum |P - P / s| (the
+// Difference term, LF:175-178, from the quotient the forward has just computed).  acc.a = sum, acc.b = bits of
+// max(-P) (the minimum, negated, so that both extremes fold with fmaxf), acc.c = max P.  NaNs drop out of the extremes
+// (fmaxf) and poison the sum, as in the loss terms.
+template <bool EXT>
+struct FwdStatsOp : OpBase<FwdStatsOp<EXT>> {
+  QMode qm;
+  using Ctx = Recip;
+  static constexpr bool kIn2 = false, kOutIsY = true, kCodes = true, kReduce = true, kAux = false;
+  __device__ static void init(Acc& a) { a.a = 0.f; a.b = __float_as_uint(-INFINITY); a.c = -INFINITY; }
+  __device__ static void combine(Acc& x, const Acc& y) {
+    x.a += y.a;
+    x.b = __float_as_uint(fmaxf(__uint_as_float(x.b), __uint_as_float(y.b)));
+    x.c = fmaxf(x.c, y.c);
+  }
+  __device__ __forceinline__ Recip prep(float s, const float4&, const Job&) const { return make_recip(s); }
+  __device__ __forceinline__ void elem(float p, float, const Recip& c, const Job&, Acc& acc, float& y, float& q) const {
+    const float t = div_by(p, c);
+    q = round_code<EXT>(t, qm);
+    y = __fmul_rn(q, c.s);
+    acc.a += fabsf(__fsub_rn(p, t));
+    acc.b = __float_as_uint(fmaxf(__uint_as_float(acc.b), -p));
+    acc.c = fmaxf(acc.c, p);
+  }
+};
+
+// Second stage of the forward statistics: one block per group, fixed order, fp64 sum.  stats[3g .. 3g+2] =
+// {min P, max P, sum |P - P/s|} (+inf, -inf, 0 for a group without ordinary elements).
+__global__ void __launch_bounds__(256) fwd_stats_finalize_kernel(const __grid_constant__ FinJob f) {
+  cudaGridDependencySynchronize();
+  const long long g = blockIdx.x;
+  const long long K = partials_per_group(f);
+  double sum = 0.0;
+  float nmin = -INFINITY, mx = -INFINITY;
+  for (long long k0 = threadIdx.x; k0 < K; k0 += 4 * 256) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long k = k0 + u * 256;
+      v[u] = (k < K) ? f.part[partial_index(f, g, k)] : make_float4(0.f, -INFINITY, -INFINITY, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sum += (double)v[u].x; nmin = fmaxf(nmin, v[u].y); mx = fmaxf(mx, v[u].z); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    nmin = fmaxf(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double ssum[8];
+  __shared__ float smin[8], smx[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { ssum[w] = sum; smin[w] = nmin; smx[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { sum += ssum[i]; nmin = fmaxf(nmin, smin[i]); mx = fmaxf(mx, smx[i]); }
+    f.ds[3 * g] = -nmin; f.ds[3 * g + 1] = mx; f.ds[3 * g + 2] = (float)sum;
+  }
+}
+
 // ------------------------------------------------------------------ K4 second stage
 // One block per group.  Walks the group's partials in index order with a fixed
 // thread->partial assignment, then a fixed shuffle/shared-memory tree: deterministic.
@@ -364,6 +427,43 @@ extern "C" int lq_fq_fwd(const float* P, const float* s, float* y, void* codes, 
   Geom g = make_geom(outer, C, inner, al);
   if ((rc = check_blocks(g))) return rc;
   return fq_fwd_launch(g, P, s, y, codes_dtype == LQ_CODES_NONE ? nullptr : codes, codes_dtype, qm, (cudaStream_t)stream);
+}
+
+extern "C" int lq_fq_fwd_stats(const float* P, const float* s, float* y, void* codes, int codes_dtype,
+                               int64_t outer, int64_t C, int64_t inner, int round_mode, float qmin, float qmax,
+                               float* stats, void* ws, size_t ws_bytes, lq_stream_t stream) {
+  int rc = check_dims(outer, C, inner);
+  if (rc) return rc;
+  if (!stats) { set_error("lq_fq_fwd_stats: null stats (use lq_fq_fwd)"); return LQ_E_NULLPTR; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (outer * C * inner == 0) {                    // empty groups: +inf, -inf, 0
+    if (C > 0) {
+      set_error("lq_fq_fwd_stats: empty tensor with C > 0 groups has no statistics"); return LQ_E_BADSHAPE;
+    }
+    return LQ_OK;
+  }
+  if (!P || !s || !y) { set_error("lq_fq_fwd_stats: null P/s/y"); return LQ_E_NULLPTR; }
+  if (codes_dtype < LQ_CODES_NONE || codes_dtype > LQ_CODES_I8 || (codes && codes_dtype == LQ_CODES_NONE)) {
+    set_error("lq_fq_fwd_stats: bad codes_dtype %d", codes_dtype); return LQ_E_BADMODE;
+  }
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  const bool al = aligned16(P) && aligned16(y) && (!codes || codes_dtype == LQ_CODES_I8 || aligned16(codes));
+  Geom g = make_geom(outer, C, inner, al);
+  if ((rc = check_blocks(g))) return rc;
+  const size_t need = align256((size_t)g.npart1 * sizeof(float4));
+  if (!ws || ws_bytes < need || !aligned16(ws)) {
+    set_error("lq_fq_fwd_stats: workspace %zu B (16-B aligned) needed, got %zu", need, ws_bytes);
+    return LQ_E_WORKSPACE;
+  }
+  Job j = make_job(g, P, s, nullptr, y, nullptr, codes_dtype == LQ_CODES_NONE ? nullptr : codes, codes_dtype,
+                   reinterpret_cast<float4*>(ws));
+  if (qm.ext) { FwdStatsOp<true> op; op.qm = qm; rc = launch_job(j, op, st); }
+  else { FwdStatsOp<false> op; op.qm = qm; rc = launch_job(j, op, st); }
+  if (rc) return rc;
+  FinJob f = make_fin(g, reinterpret_cast<const float4*>(ws), stats, s, 0.f);
+  f.nlin = 0;
+  return launch_after(fwd_stats_finalize_kernel, dim3((unsigned)g.C), dim3(256), st, "forward statistics finalize launch", f);
 }
 
 extern "C" int lq_fq_bwd_threshold(const float* dy, const float* P, const float* s, float penalty_threshold,

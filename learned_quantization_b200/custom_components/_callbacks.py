@@ -60,7 +60,10 @@ class NestedScaleTrackingCallback:
         self.log_file_path_qb = f"{t}/Quantized_{bias_name}_{bshape}_{bs}_{bss}.log"
         self.log_file_path_qk_unique = f"{t}/Unique_quantized_{kernel_name}_{kshape}_{ks}_{kss}.log"
         self.log_file_path_qb_unique = f"{t}/Unique_quantized_{bias_name}_{bshape}_{bs}_{bss}.log"
-        self.log_file_path_qk_initial = f"{b0}/Initial_Quantized_{kernel_name}_{kshape}__{ks}__{kss}.log"
+        # the IMAGENETTE / CIFAR-10 files join this one name with double underscores (custom_callbacks.py:43), the MNIST file
+        # (dense layers, :43 there) with single ones
+        sep = "_" if dense else "__"
+        self.log_file_path_qk_initial = f"{b0}/Initial_Quantized_{kernel_name}_{kshape}{sep}{ks}{sep}{kss}.log"
         self.log_file_path_qb_initial = f"{b0}/Initial_Quantized_{bias_name}_{bshape}_{bs}_{bss}.log"
         self.log_file_path_qk_initial_unique = f"{b0}/Unique_initial_quantized_{kernel_name}_{kshape}_{ks}_{kss}.log"
         self.log_file_path_qb_initial_unique = f"{b0}/Unique_initial_quantized_{bias_name}_{bshape}_{bs}_{bss}.log"

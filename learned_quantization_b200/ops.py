@@ -189,6 +189,24 @@ def fq_fwd(P: torch.Tensor, s: torch.Tensor, layout=None, *, codes_dtype: Option
     return y if codes is None else (y, codes)
 
 
+def fq_fwd_stats(P: torch.Tensor, s: torch.Tensor, layout=None, *, round_mode: int = _lib.LQ_ROUND_FLOOR,
+                 qmin: float = NEG_INF, qmax: float = POS_INF, out: Optional[torch.Tensor] = None):
+    """(y, stats): the forward and, from the same pass over P, stats[g] = {min P, max P, sum |P - P/s|} per group
+    (float32 [C, 3]) -- what max |q|, the MaxBin term and the Difference term are functions of."""
+    _require_cuda(P, s)
+    layout = layout or tensor_layout(P, s.shape)
+    y = torch.empty_like(P) if out is None else out
+    if not same_layout(y, P):
+        raise ValueError("out must be laid out in memory like P")
+    stats = torch.empty((layout[1], 3), dtype=torch.float32, device=P.device)
+    ws = workspace(workspace_bytes([make_desc(layout=layout)], _lib.LQ_PHASE_BWD), P.device)
+    with torch.cuda.device(P.device):
+        check(lib.lq_fq_fwd_stats(P.data_ptr(), s.data_ptr(), y.data_ptr(), None, _lib.LQ_CODES_NONE,
+                                  layout[0], layout[1], layout[2], round_mode, qmin, qmax,
+                                  stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return y, stats
+
+
 def fq_bwd_threshold(dy: torch.Tensor, P: torch.Tensor, s: torch.Tensor, penalty_threshold: float,
                      layout=None, *, write_dx: bool = False,
                      round_mode: int = _lib.LQ_ROUND_FLOOR, qmin: float = NEG_INF, qmax: float = POS_INF):

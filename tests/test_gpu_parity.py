@@ -471,6 +471,31 @@ def test_int8_codes_wrap_like_reference_export(lq):
     assert np.array_equal(host(codes), o.codes_int8(P, s))
 
 
+@pytest.mark.parametrize("shape,s_shape", LAYOUTS[:10] + [((1 << 22,), (1,)), ((4096, 512), (1, 512))])
+def test_forward_statistics_are_by_products_of_the_same_pass(lq, shape, s_shape):
+    """lq_fq_fwd_stats: y bit-exact as ever; per group min P / max P exact, sum |P - P/s| within 1e-5 of
+    the oracle's terms summed in fp64; and the quantities the callbacks / loss terms derive from them."""
+    ops = lq.ops
+    rng = np.random.default_rng(31)
+    P = rng.normal(0, 0.05, size=shape).astype(np.float32)
+    s = rng.uniform(5e-3, 2e-2, size=s_shape).astype(np.float32)
+    y, st = ops.fq_fwd_stats(dev(P), dev(s))
+    q_ref, y_ref = o.fq_forward(P, s)
+    assert bits_equal(host(y), y_ref)
+    st = host(st)
+    outer, C, inner = o.group_layout(shape, s_shape)
+    Pg = P.reshape(outer, C, inner)
+    sg = np.broadcast_to(s, shape).reshape(outer, C, inner) if len(s_shape) == len(shape) else np.full((outer, C, inner), s.reshape(-1)[0], np.float32)
+    assert np.array_equal(st[:, 0], Pg.min(axis=(0, 2))) and np.array_equal(st[:, 1], Pg.max(axis=(0, 2)))
+    terms = np.abs(Pg - Pg / sg).astype(np.float32)
+    assert rel_err(st[:, 2], terms.astype(np.float64).sum(axis=(0, 2))) < TOL
+    # max |q| of custom_callbacks.py:84-129 and MaxBin's per-group term (LF:90-94) from the two extremes
+    s1 = sg[0, :, 0]
+    max_abs_q = np.maximum(np.abs(np.floor(st[:, 0] / s1)), np.abs(np.floor(st[:, 1] / s1)))
+    assert np.array_equal(max_abs_q, np.abs(q_ref.reshape(outer, C, inner)).max(axis=(0, 2)))
+    assert np.array_equal(np.maximum(np.abs(st[:, 0]), np.abs(st[:, 1])) / s1, (np.abs(Pg) / sg).max(axis=(0, 2)))
+
+
 def test_multi_tensor_equals_single(lq):
     ops = lq.ops
     rng = np.random.default_rng(11)

@@ -518,3 +518,62 @@ def test_mnist_training_steps_follow_the_oracle(lq):
             # Adam's first steps move every weight by ~lr whatever the gradient's size: compare on that scale
             assert float(np.max(np.abs(got_P[k] - P[k]))) <= 0.02 * lr, (it, k)
             assert float(np.max(np.abs(got_S[k] - S[k]))) <= 0.02 * lr, (it, k)
+
+
+# ------------------------------------------------------------------ f4: the reference's own callbacks as the oracle
+@pytest.mark.parametrize("kind", ["conv", "dense"])
+def test_callbacks_write_what_the_reference_callbacks_write(lq, kind, tmp_path):
+    """tests/golden/callback_logs.* = every file the reference's custom_callbacks.py (run unmodified on the TF shim,
+    tests/golden/make_callback_golden.py) wrote for one conv / one dense layer over on_train_begin, two epochs and
+    on_train_end.  The drop-in callbacks, fed the same parameters from device memory, must write the same tree:
+    same file names, same bytes -- so whatever parses the reference's logs (utils/plot_scripts.py, checked on
+    the fixture by tests/test_callback_logs.py) parses ours."""
+    import json
+    from learned_quantization_b200 import RandomNormal
+    from learned_quantization_b200.custom_components import _impl
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_callbacks as cbs
+    from learned_quantization_b200.nested_quantization_layer.custom_components import custom_layers as nq
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gold, "callback_logs.json")) as f:
+        fx = json.load(f)
+    arr = np.load(os.path.join(gold, "callback_logs.npz"))
+    _impl._UIDS.clear()                              # Keras auto-names start afresh, as in the fixture run
+    init = RandomNormal(seed=1)
+    if kind == "conv":
+        layer = nq.CustomConv2DLayer(seed=1, penalty_threshold=1e-3, orientation="channelwise", initializer=init, filters=8,
+                                     kernel_size=(3, 3), strides=(1, 1), padding="same", name="x", regularizer=None).cuda()
+        layer(torch.zeros(1, 5, 5, 4, device="cuda"))
+        param, qk = layer.kernel, layer.nested_q_k_layer
+    else:
+        layer = nq.CustomDenseLayer(seed=1, units=6, penalty_threshold=1e-3, orientation="rowwise", initializer=init,
+                                    name="x", regularizer=None).cuda()
+        layer(torch.zeros(1, 20, device="cuda"))
+        param, qk = layer.W, layer.nested_q_w_layer
+    assert layer.name == fx["layer_names"][kind]
+
+    def stage(i):
+        with torch.no_grad():
+            param.copy_(dev(arr[f"{kind}/stage{i}/K"])); layer.b.copy_(dev(arr[f"{kind}/stage{i}/b"]))
+            qk.scale.copy_(dev(arr[f"{kind}/stage{i}/sK"])); layer.nested_q_b_layer.scale.copy_(dev(arr[f"{kind}/stage{i}/sb"]))
+    run = str(tmp_path / "run")
+    stage(0)
+    cb = cbs.NestedScaleTrackingCallback(layer, run)
+    cb.on_train_begin()
+    for epoch in (0, 1):
+        stage(epoch + 1)
+        cb.on_epoch_end(epoch)
+    cb.on_train_end()
+    acc = cbs.AccuracyLossTrackingCallBack(run)
+    for epoch, logs in enumerate(({"val_accuracy": 0.5, "val_loss": 1.25, "accuracy": 0.4375, "loss": 1.5},
+                                  {"val_accuracy": 0.625, "val_loss": 1.0, "accuracy": 0.5625, "loss": 1.125})):
+        acc.on_epoch_end(epoch, logs)
+    got = {}
+    for root, _, fs in os.walk(run):
+        for fn in fs:
+            p = os.path.join(root, fn)
+            with open(p) as fh:
+                got[os.path.relpath(p, run)] = fh.read()
+    want = fx["files"][kind]
+    assert sorted(got) == sorted(want)
+    for k in sorted(want):
+        assert got[k] == want[k], k
