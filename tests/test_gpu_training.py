@@ -577,3 +577,43 @@ def test_callbacks_write_what_the_reference_callbacks_write(lq, kind, tmp_path):
     assert sorted(got) == sorted(want)
     for k in sorted(want):
         assert got[k] == want[k], k
+
+
+# ------------------------------------------------------------------ f1 against an independent implementation
+@pytest.mark.parametrize("kind", ["adam", "sgd_nesterov"])
+def test_fused_optimizers_equal_torch_optim(lq, kind):
+    """lq_opt_adam / lq_opt_sgd against torch.optim (float64) through the exact mappings of
+    tests/test_optimizer_crosscheck.py (m = -lr * buf; eps' = eps / sqrt(1 - beta2^t); Keras' decoupled weight decay by
+    hand): an implementation of the update rules that shares nothing with the oracle's restatement."""
+    ops = lq.ops
+    rng = np.random.default_rng(12)
+    shapes = [(3, 3, 16, 32), (32,), (257,), (64, 10)]
+    p0 = [rng.normal(0, 0.05, sh).astype(np.float32) for sh in shapes]
+    ps = [dev(a) for a in p0]
+    gs = [torch.zeros_like(p) for p in ps]
+    ws = [torch.tensor(a, dtype=torch.float64, device="cuda", requires_grad=True) for a in p0]
+    steps, b1, b2, eps = 12, 0.9, 0.999, 1e-7
+    if kind == "adam":
+        lr, wd = 1e-4, 0.0
+        table = ops.OptimizerTable(ps, gs, adam=True)
+        opt = torch.optim.Adam(ws, lr=lr, betas=(b1, b2), eps=eps)
+    else:
+        lr, wd = 0.1, 5e-4
+        table = ops.OptimizerTable(ps, gs, adam=False, momentum=True, weight_decay=wd)
+        opt = torch.optim.SGD(ws, lr=lr, momentum=0.9, nesterov=True)
+    for t in range(1, steps + 1):
+        for g, w in zip(gs, ws):
+            g.copy_(dev((rng.normal(0, 1e-2, tuple(g.shape)) * (1 + 0.1 * t)).astype(np.float32)))
+            w.grad = g.to(torch.float64)
+        if kind == "adam":
+            ops.opt_adam(table, lr, t, b1, b2, eps)
+            opt.param_groups[0]["eps"] = eps / np.sqrt(1.0 - b2 ** t)
+        else:
+            ops.opt_sgd(table, lr, 0.9, True)
+            with torch.no_grad():
+                for w in ws:
+                    w.mul_(1.0 - lr * wd)
+        opt.step()
+    for a, p, w in zip(p0, ps, ws):
+        got, want = p.detach().cpu().numpy().astype(np.float64) - a, w.detach().cpu().numpy() - a
+        assert np.max(np.abs(got - want)) <= 5e-5 * np.max(np.abs(want)), kind
