@@ -236,6 +236,10 @@ int lq_dp_destroy(lq_dp_t* dp);
 typedef struct lq_p2p lq_p2p_t;
 int lq_p2p_create(int rank, int world, int64_t max_groups, lq_p2p_t** out, void* out_handle64);
 int lq_p2p_connect(lq_p2p_t* p, const void* handles64_all);
+/* same-process peers instead of IPC handles (one process driving several devices, or several "ranks" on one
+ * device on different streams -- how the single-GPU tests exercise the exchange): bufs[r] = lq_p2p_buffer of rank r */
+int lq_p2p_buffer(lq_p2p_t* p, void** out);
+int lq_p2p_connect_ptrs(lq_p2p_t* p, const void* const* bufs);
 int lq_fq_bwd_threshold_finish_p2p(lq_p2p_t* p, const double* local_stats, int64_t C, float penalty_threshold,
                                    double n_per_group, float* ds, lq_stream_t stream);
 int lq_p2p_error(lq_p2p_t* p, int* out_flag);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "lq_debug_divcheck": (_I, [_P, _I64, C.c_uint32, _P, _P]),
     "lq_p2p_create": (_I, [_I, _I, _I64, C.POINTER(_P), _P]),
     "lq_p2p_connect": (_I, [_P, _P]),
+    "lq_p2p_buffer": (_I, [_P, C.POINTER(_P)]),
+    "lq_p2p_connect_ptrs": (_I, [_P, C.POINTER(_P)]),
     "lq_fq_bwd_threshold_finish_p2p": (_I, [_P, _P, _I64, _F, C.c_double, _P, _P]),
     "lq_p2p_error": (_I, [_P, C.POINTER(_I)]),
     "lq_p2p_destroy": (_I, [_P]),

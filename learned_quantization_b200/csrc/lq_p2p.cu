@@ -144,6 +144,23 @@ extern "C" int lq_p2p_connect(lq_p2p_t* p, const void* handles64_all) {
   return LQ_OK;
 }
 
+extern "C" int lq_p2p_connect_ptrs(lq_p2p_t* p, const void* const* bufs) {
+  if (!p || !bufs) { set_error("lq_p2p_connect_ptrs: null argument"); return LQ_E_NULLPTR; }
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    if (!bufs[r]) { set_error("lq_p2p_connect_ptrs: null buffer for rank %d", r); return LQ_E_NULLPTR; }
+    p->peer[r] = const_cast<void*>(bufs[r]);
+  }
+  p->connected = true;
+  return LQ_OK;
+}
+
+extern "C" int lq_p2p_buffer(lq_p2p_t* p, void** out) {
+  if (!p || !out) { set_error("lq_p2p_buffer: null argument"); return LQ_E_NULLPTR; }
+  *out = p->buf;
+  return LQ_OK;
+}
+
 extern "C" int lq_fq_bwd_threshold_finish_p2p(lq_p2p_t* p, const double* local_stats, int64_t C, float penalty_threshold,
                                               double n_per_group, float* ds, lq_stream_t stream) {
   if (!p || !local_stats || !ds) { set_error("lq_fq_bwd_threshold_finish_p2p: null argument"); return LQ_E_NULLPTR; }

@@ -277,3 +277,67 @@ def test_copy_engine_allreduce_is_the_rank_order_mean(lq, world, n):
         torch.cuda.synchronize()
         for h in hs:
             check(lib.lq_dpx_destroy(h))
+
+
+# ------------------------------------------------------------------ the sharded microbench's fused exchange + finish
+def _p2p_world(world, C_):
+    from learned_quantization_b200._lib import check, lib
+    hs, bufs = [], []
+    for r in range(world):
+        h, handle, buf = C.c_void_p(), C.create_string_buffer(64), C.c_void_p()
+        check(lib.lq_p2p_create(r, world, C_, C.byref(h), handle))
+        check(lib.lq_p2p_buffer(h, C.byref(buf)))
+        hs.append(h); bufs.append(buf.value)
+    ptrs = (C.c_void_p * world)(*bufs)
+    for h in hs:
+        check(lib.lq_p2p_connect_ptrs(h, ptrs))
+    return hs
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_p2p_finish_equals_gather_then_finish(lq, world):
+    """lq_fq_bwd_threshold_finish_p2p (statistics pushed into every rank's slots, flags, fold in rank order) against
+    lq_fq_bwd_threshold_finish on the gathered statistics: bit for bit, on every rank, twice (epoch parity)."""
+    from learned_quantization_b200._lib import check, lib
+    ops = lq.ops
+    C_ = 300
+    rng = np.random.default_rng(40 + world)
+    hs = _p2p_world(world, C_)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for rep in range(3):
+            stats = [torch.from_numpy(np.stack([rng.normal(0, 1, C_), rng.integers(0, 3, C_).astype(np.float64),
+                                                rng.integers(0, 50, C_).astype(np.float64)], axis=1)).cuda().contiguous()
+                     for _ in range(world)]
+            want = ops.fq_bwd_threshold_finish(torch.stack(stats), 1e-3, 12345.0)
+            outs = [torch.empty(C_, device="cuda") for _ in range(world)]
+            torch.cuda.synchronize()
+            for h, st, out, sm in zip(hs, stats, outs, streams):
+                check(lib.lq_fq_bwd_threshold_finish_p2p(h, st.data_ptr(), C_, 1e-3, 12345.0, out.data_ptr(), sm.cuda_stream))
+            torch.cuda.synchronize()
+            for h, out in zip(hs, outs):
+                flag = C.c_int(0)
+                check(lib.lq_p2p_error(h, C.byref(flag)))
+                assert flag.value == 0
+                assert bits_equal(out.cpu().numpy(), want.cpu().numpy()), rep
+    finally:
+        torch.cuda.synchronize()
+        for h in hs:
+            check(lib.lq_p2p_destroy(h))
+
+
+def test_p2p_finish_times_out_without_its_peer(lq):
+    from learned_quantization_b200._lib import check, lib
+    C_ = 64
+    hs = _p2p_world(2, C_)
+    try:
+        st = torch.ones((C_, 3), dtype=torch.float64, device="cuda")
+        out = torch.zeros(C_, device="cuda")
+        check(lib.lq_fq_bwd_threshold_finish_p2p(hs[0], st.data_ptr(), C_, 1e-3, 10.0, out.data_ptr(), 0))   # rank 1 never launches
+        flag = C.c_int(0)
+        check(lib.lq_p2p_error(hs[0], C.byref(flag)))          # synchronises: ~2 s
+        assert flag.value == 1 and bool(torch.isnan(out).all())
+    finally:
+        torch.cuda.synchronize()
+        for h in hs:
+            check(lib.lq_p2p_destroy(h))

@@ -29,14 +29,26 @@ def host(t):
     return t.detach().cpu().numpy()
 
 
-def ds_close(got, ref, tol=TOL):
+WORST = {"ds": 0.0}      # largest per-group scale-gradient error seen by ds_close in this session (printed by the last test)
+
+
+def ds_err(got, ref):
+    """Per-group relative error of a scale gradient: |got - ref| / max(|ref|, 1e-6 * max|ref|), NaN == NaN."""
     got = np.asarray(got, np.float64).reshape(-1)
     ref = np.asarray(ref, np.float64).reshape(-1)
-    scale = max(float(np.max(np.abs(ref))), 1e-30) if ref.size else 1.0
-    # per-element relative error, with an absolute floor relative to the largest entry
-    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3 * scale)
+    if not ref.size:
+        return 0.0
+    scale = max(float(np.max(np.abs(ref))), 1e-30)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6 * scale)
     err = np.where(np.isnan(got) & np.isnan(ref), 0.0, err)
-    return float(np.max(err)) <= tol if err.size else True
+    return float(np.max(err))
+
+
+def ds_close(got, ref, tol=TOL):
+    e = ds_err(got, ref)
+    if np.isfinite(e):
+        WORST["ds"] = max(WORST["ds"], e)
+    return e <= tol
 
 
 # ------------------------------------------------------------------ golden fixtures
@@ -158,6 +170,7 @@ def test_golden_host_layers(lq, golden):
     from learned_quantization_b200.custom_loss_terms.custom_components import custom_layers as cl
     from learned_quantization_b200.paper_implementation.custom_components import custom_layers as pi
     mods = {"NQ": nq, "CL": cl, "PI": pi}
+    ops_ = lq.ops
     # the fixtures are fp32 CPU convolutions; cuDNN would otherwise pick TF32 (conv is not our path)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -190,8 +203,16 @@ def test_golden_host_layers(lq, golden):
             r = golden[f"{cid}/ds{i}"]
             got = host(getattr(layer, n).scale.grad)
             assert got.shape == r.shape
-            # ds depends on dy only through thresholded ratios; dy differs from the fixture in the last bits
+            # end to end ds depends on dy only through thresholded ratios, and cuDNN's dy differs from the fixture's
+            # in the last bits: a loose bound here ...
             assert float(np.max(np.abs(got - r))) <= 2e-3 * max(float(np.max(np.abs(r))), 1e-30), (c, n, got, r)
+            # ... and the operator itself held to 1e-5 per group on the FIXTURE'S OWN dy (the gradient the reference's
+            # layer handed to its custom_grad is the parameter gradient it returned: dP = dy, NQ:118)
+            if c["module"] == "NQ":
+                q = getattr(layer, n)
+                _, ds_direct = ops_.fq_bwd_threshold(dev(golden[f"{cid}/dw{i}"]), params[i].detach(), q.scale.detach(),
+                                                     float(q.penalty_threshold))
+                assert ds_close(host(ds_direct).reshape(r.shape), r), (c, n, host(ds_direct), r)
 
 
 # ------------------------------------------------------------------ randomized vs oracle
@@ -502,6 +523,7 @@ def test_multi_tensor_equals_single(lq):
     shapes = [((3, 3, 16, 32), (1, 1, 16, 1)), ((32,), (1,)), ((7, 7, 3, 64), (1, 1, 3, 1)), ((64,), (1,)),
               ((3, 3, 64, 128), (1, 1, 64, 1)), ((128,), (1,)), ((784, 128), (784, 1)), ((1, 1, 64, 128), (1, 1, 64, 1))]
     shapes = shapes * 8          # 64 tensors: more than one kernel-parameter table
+    shapes.append(((3, 3, 1024, 512), (1,)))      # one group with 4608 partials: the two-level second stage of lq_mt_fq_bwd
     Ps = [dev(rng.normal(0, 0.05, size=sh).astype(np.float32)) for sh, _ in shapes]
     ss = [dev(rng.uniform(5e-3, 2e-2, size=ssh).astype(np.float32)) for _, ssh in shapes]
     dys = [dev(rng.normal(0, 1e-3, size=sh).astype(np.float32)) for sh, _ in shapes]
@@ -808,3 +830,9 @@ def test_more_than_2_pow_31_elements(lq, layout):
         grp = host(((idx // inner) % C).to(torch.int32))
         _, y_ref = o.fq_forward(host(Pd[lo:hi]), host(sd)[grp])
         assert bits_equal(host(y[lo:hi]), y_ref), m
+
+
+def test_zz_worst_scale_gradient_error_of_the_session(lq):
+    """Not a check of its own: prints the largest per-group relative ds error ds_close met (bound: 1e-5)."""
+    print(f"\nworst per-group scale-gradient error this session: {WORST['ds']:.3e} (tolerance {TOL:.0e}, floor 1e-6 * max|ds|)")
+    assert WORST["ds"] <= TOL
