@@ -87,15 +87,50 @@ class ClockSampler:
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
-    committed ncu --set full capture summary (profiles/traffic.json); None when absent."""
+    """(bytes, note): dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    summary of an `ncu --set full` capture (profiles/traffic.json, written by tools/refresh_traffic.py) -- reported only
+    while the hash of the kernel sources stored with the capture still matches the tree: a stale capture reads null."""
+    import hashlib
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
-        return t["traffic_bytes_per_launch"] if t.get("workload") == WORKLOAD else None
-    except (OSError, ValueError, KeyError):
-        return None
+        if t.get("workload") != WORKLOAD:
+            return None, "profiles/traffic.json is for another workload"
+        h = hashlib.sha256()
+        for name in t["sources"]:
+            with open(os.path.join(ROOT, "learned_quantization_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        if h.hexdigest() != t["source_sha256"]:
+            return None, f"capture of commit {t.get('commit_at_capture')} predates the current kernel sources: re-run tools/refresh_traffic.py"
+        return t["traffic_bytes_per_launch"], f"ncu --set full at commit {t.get('commit_at_capture')}, kernel sources unchanged since"
+    except (OSError, ValueError, KeyError) as e:
+        return None, f"no usable profiles/traffic.json ({type(e).__name__})"
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process -- and with it the pinned host buffers it allocates from now on (first touch) -- to the NUMA
+    node its GPU hangs off: with 8 ranks streaming 0.8 GB per step each through host memory, remote-node buffers halve
+    what the root complexes deliver."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": None, "bound": False}
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "numa_node": node, "cpus": len(cpus), "bound": bool(cpus)}
+    except (OSError, ValueError, AttributeError) as e:
+        return {"numa_node": None, "bound": False, "why": f"{type(e).__name__}: {e}"}
 
 
 def measured_peak():
@@ -235,6 +270,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import learned_quantization_b200 as lq
@@ -383,17 +419,35 @@ def run_ours(args):
         ops.host_fq_fwd_bwd(hP, hs, hdy, LAMBDA, hy, hds, LAYOUT, hws)
     barrier()
     e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    # what the box can do for this traffic pattern with every rank at it at once: the step's H2D (P, dy) and D2H (y)
+    # bytes as plain pinned copies on two streams, nothing else
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    dP_, ddy_ = sets[0]
+
+    def copies():
+        with torch.cuda.stream(up):
+            dP_.copy_(hP.view_as(dP_), non_blocking=True); ddy_.copy_(hdy.view_as(ddy_), non_blocking=True)
+        with torch.cuda.stream(down):
+            hy.copy_(y.view_as(hy), non_blocking=True)
+    copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copies()
+    barrier()
+    pcie_ms = (time.perf_counter() - t0) / 3 * 1e3
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms, pcie_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms = t.tolist()
+    total_ms, fwd_ms, bwd_ms, e2e_ms, instr_ms, pcie_ms = t.tolist()
     if rank == 0:
         step_ms = total_ms / args.steps
         value = (BYTES_FWD + BYTES_BWD) * n * world / (step_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         achieved = BYTES_BWD * n / (bwd_ms * 1e-3) / 1e9
+        traffic, traffic_note = ncu_traffic()
         cb = cpu_baseline() if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -415,12 +469,18 @@ def run_ours(args):
             "fwd_GBps": BYTES_FWD * n / (fwd_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": "row_kernel<BwdThresholdOp> (+ finalize_warp_kernel, its second stage)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "frac_of_8TBps_spec": achieved / 8000.0,
+                         "traffic": traffic, "traffic_source": traffic_note,
                          "algorithmic_bytes_per_launch": BYTES_BWD * n},
             "e2e": {"value": (BYTES_FWD + BYTES_BWD) * n * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n + 4 * LAYOUT[1],
                     "d2h_bytes_per_step": 4 * n + 4 * LAYOUT[1],
-                    "api": "lq_host_fq_fwd_bwd (pinned host P, s, dy in; host y, ds out; dX is dy itself)"},
+                    "api": "lq_host_fq_fwd_bwd (pinned host P, s, dy in; host y, ds out; dX is dy itself)",
+                    "pcie_bound": {"value": (BYTES_FWD + BYTES_BWD) * n * world / (pcie_ms * 1e-3) / 1e9, "unit": UNIT,
+                                   "ms_per_step": pcie_ms,
+                                   "what": "the same bytes as bare pinned copies (H2D and D2H on two streams), all ranks at once"},
+                    "frac_of_pcie_bound": pcie_ms / e2e_ms,
+                    "numa": numa},
             "gpu_launches": (3 if world == 1 else 4) * args.steps,
             "clocks": clocks,
         }
@@ -650,6 +710,9 @@ def run_qat(args, rank, world, local, key="qat"):
         for _ in range(3):
             run(x, y)
     barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -657,6 +720,7 @@ def run_qat(args, rank, world, local, key="qat"):
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1) / steps
+    qat_clocks = sampler.stop() if rank == 0 else None
     # end to end: every step's batch comes from pinned host memory and every step's loss is read back.
     # The H2D copy of batch i+1 is issued on a copy stream BEFORE step i is launched, so it overlaps step i
     # (a data loader's prefetch); each step still pays for exactly one batch copy inside the timed region.
@@ -688,6 +752,34 @@ def run_qat(args, rank, world, local, key="qat"):
         loss_host = float(loss)
     barrier()
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    # N > 1, default configuration only: the same captured step WITHOUT any exchange (N independent replicas running
+    # at the same time on the same box) -- what separates the cost of the exchange from what eight busy GPUs in one
+    # chassis cost each other (clocks, power), which no exchange design can change
+    replica_ms = 0.0
+    if world > 1 and key == "qat" and not args.qat_eager and not args.qat_skip_exchange:
+        real_exchange = step._exchange
+        early = getattr(step, "_early", None)
+
+        def local_only(scale_backward=None):
+            with torch.no_grad():
+                (scale_backward or step._scale_backward)()
+        step._exchange = local_only
+        if early is not None:
+            step._early = []
+        step.capture(x, y, warmup=3)
+        for _ in range(3):
+            step.replay(x, y)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(steps):
+            step.replay(x, y)
+        r1.record()
+        barrier()
+        replica_ms = r0.elapsed_time(r1) / steps
+        step._exchange = real_exchange
+        if early is not None:
+            step._early = early
     # the gradient exchange alone (N > 1): K launches between two events on the step's stream
     exch_ms = 0.0
     if world > 1:
@@ -701,10 +793,10 @@ def run_qat(args, rank, world, local, key="qat"):
         x1.record()
         barrier()
         exch_ms = x0.elapsed_time(x1) / steps
-    t = torch.tensor([dev_ms, e2e_ms, exch_ms], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_ms, exch_ms, replica_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, exch_ms = t.tolist()
+    dev_ms, e2e_ms, exch_ms, replica_ms = t.tolist()
     n_q = sum(p.numel() for p in step.bank.params)
     name = {"imagenette": f"imagenette_resnet_{variant}_channelwise_224" + (f"_{cfg['loss']}" if variant == "custom_loss" else ""),
             "cifar_paper": "cifar10_paper_resnet18_channelwise_32", "mnist": "mnist_mlp_nested_per_tensor"}[model]
@@ -732,7 +824,11 @@ def run_qat(args, rank, world, local, key="qat"):
                                      "lq_dpx_exchange": (2 if threshold else 1) if peer else 0,
                                      ("lq_opt_sgd" if cifar else "lq_opt_adam"): -(-len(step.table.params) // 56),
                                      "lq_dp_allreduce": 1 if (world > 1 and not peer) else 0},
-           "last_loss": loss_host}
+           "last_loss": loss_host, "clocks": qat_clocks}
+    if replica_ms:
+        out["independent_replicas"] = {"ms_per_step": replica_ms, "value": batch * world / (replica_ms * 1e-3),
+                                       "dp_over_replicas": replica_ms / dev_ms,
+                                       "what": "the same step on the same N GPUs at the same time with the exchange removed"}
     if world > 1:
         nbytes = step.bucket.n_exact * 4
         out["exchange"] = {"ms": exch_ms, "bytes": nbytes,
@@ -876,7 +972,7 @@ def main():
                     help="with --only-qat: which training configuration to time")
     ap.add_argument("--qat-skip-exchange", action="store_true", help="diagnostic: N > 1 without any gradient exchange")
     ap.add_argument("--qat-no-overlap", action="store_true", help="N > 1: exchange all gradients after the backward")
-    ap.add_argument("--qat-late-blocks", type=int, default=32,
+    ap.add_argument("--qat-late-blocks", type=int, default=16,
                     help="N > 1: grid of the exchange that is started while the backward is still running")
     ap.add_argument("--qat-comm", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange of the QAT step (fused peer-memory kernel, or ncclAllReduce)")

@@ -205,6 +205,17 @@ int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float* hdy, float
                        float* hy, float* hdX, float* hds,
                        int64_t outer, int64_t C, int64_t inner,
                        void* dev_ws, size_t dev_ws_bytes);
+/* The same with an explicit handle (the pipeline's streams and events, created once; the handle-less form keeps one
+ * per device for the life of the process) and ordered after the caller's stream: with order_after != 0 every staged
+ * copy waits for the work enqueued on `after` at the time of the call (what last used dev_ws).  One call at a time
+ * per handle. */
+typedef struct lq_host lq_host_t;
+int lq_host_create(lq_host_t** out);
+int lq_host_destroy(lq_host_t* h);
+int lq_host_fq_fwd_bwd_on(lq_host_t* h, const float* hP, const float* hs, const float* hdy, float penalty_threshold,
+                          float* hy, float* hdX, float* hds,
+                          int64_t outer, int64_t C, int64_t inner,
+                          void* dev_ws, size_t dev_ws_bytes, lq_stream_t after, int order_after);
 
 /* Diagnostics: checks on the device that the kernels' hoisted-reciprocal division equals
  * IEEE division (the bit-exactness the forward is graded on, NQ:56-58 tf.truediv) for every

@@ -67,6 +67,9 @@ SIGNATURES = {
     "lq_mt_fq_bwd": (_I, [_DESCS, _I, _F, _I, _I, _F, _F, _P, _SZ, _P]),
     "lq_host_workspace_bytes": (_I, [_I64, _I64, _I64, C.POINTER(_SZ)]),
     "lq_host_fq_fwd_bwd": (_I, [_P, _P, _P, _F, _P, _P, _P, _I64, _I64, _I64, _P, _SZ]),
+    "lq_host_create": (_I, [C.POINTER(_P)]),
+    "lq_host_destroy": (_I, [_P]),
+    "lq_host_fq_fwd_bwd_on": (_I, [_P, _P, _P, _P, _F, _P, _P, _P, _I64, _I64, _I64, _P, _SZ, _P, _I]),
     "lq_colsum_workspace_bytes": (_I, [_I64, _I64, C.POINTER(_SZ)]),
     "lq_colsum": (_I, [_P, _I64, _I64, _P, _P, _SZ, _P]),
     "lq_code_range": (_I, [_P, _P, _I64, _I64, _I64, _I, _F, _F, _P, _P, _SZ, _P]),

@@ -6,6 +6,7 @@
 // NCCL (the CPU test tier), and (b) inside a torch process we bind to the libnccl.so.2 that
 // torch has already mapped instead of a second copy.
 #include <dlfcn.h>
+#include <stdio.h>
 #include <string.h>
 #include <mutex>
 #include "lq_common.cuh"
@@ -31,6 +32,7 @@ struct NcclApi {
 
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
+static char g_nccl_dlerr[256] = "";
 
 static void load_nccl() {
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -38,7 +40,11 @@ static void load_nccl() {
     g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (g_nccl.handle) break;
   }
-  if (!g_nccl.handle) return;
+  if (!g_nccl.handle) {
+    const char* e = dlerror();                 // read ONCE: the call clears the error
+    snprintf(g_nccl_dlerr, sizeof(g_nccl_dlerr), "%s", e ? e : "libnccl.so.2 not found");
+    return;
+  }
   g_nccl.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(g_nccl.handle, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
@@ -50,7 +56,7 @@ static void load_nccl() {
 
 static int need_nccl() {
   std::call_once(g_nccl_once, load_nccl);
-  if (!g_nccl.ok) { set_error("NCCL not available: %s", dlerror() ? dlerror() : "libnccl.so.2 not found"); return LQ_E_NCCL; }
+  if (!g_nccl.ok) { set_error("NCCL not available: %s", g_nccl_dlerr[0] ? g_nccl_dlerr : "a required symbol is missing"); return LQ_E_NCCL; }
   return LQ_OK;
 }
 
@@ -85,7 +91,21 @@ using namespace lq;
 struct lq_dp {
   ncclComm_t comm;
   int rank, world;
+  int device;      // the device the communicator was created on: every collective must be issued with it current
 };
+
+// A communicator is bound to the device that was current at lq_dp_init; a collective issued from another device
+// would enqueue on the wrong GPU's stream.  Refuse instead of guessing.
+static int dp_check_device(const lq_dp* dp, const char* who) {
+  int dev = -1;
+  int rc = cuda_fail(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  if (dev != dp->device) {
+    set_error("%s: the communicator belongs to device %d but device %d is current", who, dp->device, dev);
+    return LQ_E_BADMODE;
+  }
+  return LQ_OK;
+}
 
 extern "C" int lq_dp_unique_id(void* out_id128) {
   if (!out_id128) { set_error("lq_dp_unique_id: null out"); return LQ_E_NULLPTR; }
@@ -104,13 +124,16 @@ extern "C" int lq_dp_init(const void* id128, int rank, int world, lq_dp_t** out)
   memcpy(&id, id128, sizeof(id));
   ncclComm_t comm = nullptr;
   if ((rc = nccl_fail(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank"))) return rc;
-  lq_dp* dp = new lq_dp{comm, rank, world};
+  int dev = 0;
+  if ((rc = cuda_fail(cudaGetDevice(&dev), "cudaGetDevice"))) { g_nccl.CommDestroy(comm); return rc; }
+  lq_dp* dp = new lq_dp{comm, rank, world, dev};
   *out = dp;
   return LQ_OK;
 }
 
 extern "C" int lq_dp_allreduce(lq_dp_t* dp, float* flat, int64_t n, float scale, lq_stream_t stream) {
   if (!dp) { set_error("lq_dp_allreduce: null communicator"); return LQ_E_NULLPTR; }
+  if (int drc = dp_check_device(dp, "lq_dp_allreduce")) return drc;
   if (n < 0) { set_error("lq_dp_allreduce: n < 0"); return LQ_E_BADSHAPE; }
   if (n == 0) return LQ_OK;
   if (!flat) { set_error("lq_dp_allreduce: null buffer"); return LQ_E_NULLPTR; }
@@ -134,6 +157,7 @@ extern "C" int lq_dp_allreduce(lq_dp_t* dp, float* flat, int64_t n, float scale,
 
 extern "C" int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_stream_t stream) {
   if (!dp) { set_error("lq_dp_allreduce_max: null communicator"); return LQ_E_NULLPTR; }
+  if (int drc = dp_check_device(dp, "lq_dp_allreduce_max")) return drc;
   if (n < 0) { set_error("lq_dp_allreduce_max: n < 0"); return LQ_E_BADSHAPE; }
   if (n == 0) return LQ_OK;
   if (!flat) { set_error("lq_dp_allreduce_max: null buffer"); return LQ_E_NULLPTR; }
@@ -142,6 +166,7 @@ extern "C" int lq_dp_allreduce_max(lq_dp_t* dp, float* flat, int64_t n, lq_strea
 
 extern "C" int lq_dp_allgather_f64(lq_dp_t* dp, const double* send, double* recv, int64_t n, lq_stream_t stream) {
   if (!dp) { set_error("lq_dp_allgather_f64: null communicator"); return LQ_E_NULLPTR; }
+  if (int drc = dp_check_device(dp, "lq_dp_allgather_f64")) return drc;
   if (n < 0) { set_error("lq_dp_allgather_f64: n < 0"); return LQ_E_BADSHAPE; }
   if (n == 0) return LQ_OK;
   if (!send || !recv) { set_error("lq_dp_allgather_f64: null buffer"); return LQ_E_NULLPTR; }

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include "lq_traverse.cuh"
 
 namespace lq {
@@ -85,10 +86,79 @@ extern "C" int lq_host_workspace_bytes(int64_t outer, int64_t C, int64_t inner, 
   return LQ_OK;
 }
 
+// Streams and events of the staged pipeline, created once (per handle) instead of per call.
+struct lq_host {
+  int device;
+  cudaStream_t st[kSlots];
+  cudaEvent_t ev_s, ev_in, ev_done[kSlots];
+  std::mutex mu;               // one call at a time per handle: the slots are shared state
+};
+
+static int host_handle_init(lq_host* h) {
+  int rc = cuda_fail(cudaGetDevice(&h->device), "lq_host: cudaGetDevice");
+  for (int i = 0; i < kSlots && !rc; ++i) {
+    rc = cuda_fail(cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking), "lq_host: stream create");
+    if (!rc) rc = cuda_fail(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming), "lq_host: event create");
+  }
+  if (!rc) rc = cuda_fail(cudaEventCreateWithFlags(&h->ev_s, cudaEventDisableTiming), "lq_host: event create");
+  if (!rc) rc = cuda_fail(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming), "lq_host: event create");
+  return rc;
+}
+
+extern "C" int lq_host_create(lq_host_t** out) {
+  if (!out) { set_error("lq_host_create: null out"); return LQ_E_NULLPTR; }
+  lq_host* h = new lq_host();
+  for (int i = 0; i < kSlots; ++i) { h->st[i] = nullptr; h->ev_done[i] = nullptr; }
+  h->ev_s = h->ev_in = nullptr;
+  const int rc = host_handle_init(h);
+  if (rc) { lq_host_destroy(h); return rc; }
+  *out = h;
+  return LQ_OK;
+}
+
+extern "C" int lq_host_destroy(lq_host_t* h) {
+  if (!h) return LQ_OK;
+  for (int i = 0; i < kSlots; ++i) {
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->st[i]) { cudaStreamSynchronize(h->st[i]); cudaStreamDestroy(h->st[i]); }
+  }
+  if (h->ev_s) cudaEventDestroy(h->ev_s);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  delete h;
+  return LQ_OK;
+}
+
+// the handle behind the handle-less entry point: one per device, created on first use, kept for the process
+static lq_host* default_handle() {
+  static std::mutex mu;
+  static lq_host* per_device[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!per_device[dev]) {
+    lq_host* h = nullptr;
+    if (lq_host_create(&h) != LQ_OK) return nullptr;
+    per_device[dev] = h;
+  }
+  return per_device[dev];
+}
+
 extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float* hdy, float penalty_threshold,
                                   float* hy, float* hdX, float* hds,
                                   int64_t outer, int64_t C, int64_t inner,
                                   void* dev_ws, size_t dev_ws_bytes) {
+  lq_host* h = default_handle();
+  if (!h) { set_error("lq_host_fq_fwd_bwd: no CUDA device / streams"); return LQ_E_CUDA; }
+  return lq_host_fq_fwd_bwd_on(h, hP, hs, hdy, penalty_threshold, hy, hdX, hds, outer, C, inner, dev_ws, dev_ws_bytes,
+                               nullptr, 0);
+}
+
+extern "C" int lq_host_fq_fwd_bwd_on(lq_host_t* h, const float* hP, const float* hs, const float* hdy, float penalty_threshold,
+                                     float* hy, float* hdX, float* hds,
+                                     int64_t outer, int64_t C, int64_t inner,
+                                     void* dev_ws, size_t dev_ws_bytes, lq_stream_t after, int order_after) {
+  if (!h) { set_error("lq_host_fq_fwd_bwd_on: null handle"); return LQ_E_NULLPTR; }
+  std::lock_guard<std::mutex> lock(h->mu);
   int rc = check_dims(outer, C, inner);
   if (rc) return rc;
   const long long n = outer * C * inner;
@@ -110,19 +180,18 @@ extern "C" int lq_host_fq_fwd_bwd(const float* hP, const float* hs, const float*
     return reinterpret_cast<float*>(base + p.off_stage + ((size_t)slot * 3 + which) * stage);
   };
 
-  cudaStream_t st[kSlots] = {};
-  cudaEvent_t ev_s = nullptr, ev_done[kSlots] = {};
-  auto cleanup = [&]() {
-    for (int i = 0; i < kSlots; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (st[i]) cudaStreamDestroy(st[i]); }
-    if (ev_s) cudaEventDestroy(ev_s);
-  };
+  cudaStream_t* st = h->st;
+  cudaEvent_t ev_s = h->ev_s;
+  cudaEvent_t* ev_done = h->ev_done;
+  auto cleanup = [&]() {};
 #define LQ_TRY(expr, what) do { if ((rc = cuda_fail((expr), what))) { cudaDeviceSynchronize(); cleanup(); return rc; } } while (0)
 #define LQ_TRY_RC(expr) do { if ((rc = (expr))) { cudaDeviceSynchronize(); cleanup(); return rc; } } while (0)
-  for (int i = 0; i < kSlots; ++i) {
-    LQ_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking), "stream create");
-    LQ_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming), "event create");
+  // `after` (order_after != 0): work the caller has enqueued on that stream -- whatever last touched dev_ws, e.g. the
+  // previous tenant of a caching allocator's block -- completes before the first staged copy
+  if (order_after) {
+    LQ_TRY(cudaEventRecord(h->ev_in, (cudaStream_t)after), "event record");
+    for (int i = 0; i < kSlots; ++i) LQ_TRY(cudaStreamWaitEvent(st[i], h->ev_in, 0), "stream wait");
   }
-  LQ_TRY(cudaEventCreateWithFlags(&ev_s, cudaEventDisableTiming), "event create");
 
   LQ_TRY(cudaMemcpyAsync(d_s, hs, (size_t)C * 4, cudaMemcpyHostToDevice, st[0]), "H2D s");
   // Zero partial = {sum 0, n_below 0, max 0}: neutral, so a tail chunk that covers fewer

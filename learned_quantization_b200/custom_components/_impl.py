@@ -191,11 +191,20 @@ class _HostLayer(nn.Module):
         if trained is not None:
             return _as_param(trained, shape, device)
         if self.initializer is None:
-            t = torch.empty(tuple(shape), dtype=torch.float32)
-            if len(shape) >= 2:
-                nn.init.xavier_uniform_(t.view(-1, shape[-1]) if len(shape) > 2 else t)   # Keras default glorot_uniform
+            # Keras' add_weight default for float weights: glorot_uniform with Keras' fans (_compute_fans): a vector
+            # has fan_in = fan_out = n, a matrix (in, out), a kernel receptive_field * (Cin, Cout)
+            shape = tuple(int(d) for d in shape)
+            if len(shape) == 1:
+                fan_in = fan_out = shape[0]
+            elif len(shape) == 2:
+                fan_in, fan_out = shape
             else:
-                t.zero_()
+                receptive = 1
+                for d in shape[:-2]:
+                    receptive *= d
+                fan_in, fan_out = receptive * shape[-2], receptive * shape[-1]
+            limit = (6.0 / max(1.0, (fan_in + fan_out))) ** 0.5
+            t = torch.empty(shape, dtype=torch.float32).uniform_(-limit, limit)
             return nn.Parameter(t.to(device))
         return _as_param(self.initializer(tuple(shape)), shape, device)
 

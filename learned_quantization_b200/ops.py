@@ -348,6 +348,20 @@ def host_workspace_bytes(layout) -> int:
     return out.value
 
 
+_HOST_HANDLES: dict = {}
+
+
+def _host_handle(device: torch.device):
+    """lq_host_create once per device: the pipeline's streams and events are reused by every call."""
+    h = _HOST_HANDLES.get(device.index)
+    if h is None:
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.lq_host_create(C.byref(h)))
+        _HOST_HANDLES[device.index] = h
+    return h
+
+
 def host_fq_fwd_bwd(hP: torch.Tensor, hs: torch.Tensor, hdy: torch.Tensor, penalty_threshold: float,
                     hy: torch.Tensor, hds: torch.Tensor, layout, dev_ws: torch.Tensor,
                     hdX: Optional[torch.Tensor] = None) -> None:
@@ -358,9 +372,11 @@ def host_fq_fwd_bwd(hP: torch.Tensor, hs: torch.Tensor, hdy: torch.Tensor, penal
     if not dev_ws.is_cuda:
         raise RuntimeError("dev_ws must be a CUDA buffer (no CPU fallback)")
     with torch.cuda.device(dev_ws.device):
-        check(lib.lq_host_fq_fwd_bwd(hP.data_ptr(), hs.data_ptr(), hdy.data_ptr(), float(penalty_threshold),
-                                     hy.data_ptr(), None if hdX is None else hdX.data_ptr(), hds.data_ptr(),
-                                     layout[0], layout[1], layout[2], dev_ws.data_ptr(), dev_ws.numel()))
+        # ordered after the current stream: dev_ws is a caching-allocator block whose previous use was enqueued there
+        check(lib.lq_host_fq_fwd_bwd_on(_host_handle(dev_ws.device), hP.data_ptr(), hs.data_ptr(), hdy.data_ptr(),
+                                        float(penalty_threshold), hy.data_ptr(),
+                                        None if hdX is None else hdX.data_ptr(), hds.data_ptr(),
+                                        layout[0], layout[1], layout[2], dev_ws.data_ptr(), dev_ws.numel(), _stream(), 1))
 
 
 # --------------------------------------------------------------------- optimizer step

@@ -98,7 +98,7 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, loss_fn: Callable, *, optimizer: str = "adam", lr: float = 1e-4,
                  momentum: float = 0.0, nesterov: bool = False, weight_decay: float = 0.0,
-                 comm: Optional[Comm] = None, ds_mode: str = "exact", overlap: bool = True, late_blocks: int = 32):
+                 comm: Optional[Comm] = None, ds_mode: str = "exact", overlap: bool = True, late_blocks: int = 16):
         """overlap (PeerComm, exact mode): start exchanging the late layers' gradients on a side stream as soon
         as the backward has produced them, while it is still working on the early layers.  late_blocks: grid of
         that early-started exchange -- it waits on NVLink, not on arithmetic, so it is given few SMs and a long

@@ -83,3 +83,19 @@ def test_grad_bucket_mirrors_parameter_memory():
     offs = [v.data_ptr() - b.flat.data_ptr() for v in b.dy + b.plain + b.ds]
     assert offs == sorted(offs) and all(o_ % 16 == 0 for o_ in offs)
     assert b.exact_part().numel() == offs[3] // 4 and b.all().numel() >= b.exact_part().numel() + 5 + 1
+
+
+def test_default_initializer_uses_keras_glorot_fans():
+    """initializer=None falls back to what Keras' add_weight would do: glorot_uniform with Keras' fans --
+    receptive_field * (Cin, Cout) for a kernel, n for a vector (biases are NOT zero-filled)."""
+    from learned_quantization_b200.custom_components import _impl
+
+    class L(_impl._HostLayer):
+        initializer = None
+    layer = L()
+    torch.manual_seed(0)
+    for shape, fans in (((3, 3, 16, 32), (9 * 16, 9 * 32)), ((784, 128), (784, 128)), ((64,), (64, 64))):
+        limit = (6.0 / sum(fans)) ** 0.5
+        w = layer._init_weight(shape, None, "cpu").detach()
+        assert tuple(w.shape) == shape and float(w.abs().max()) <= limit
+        assert float(w.abs().max()) > 0.8 * limit and abs(float(w.mean())) < 0.2 * limit
