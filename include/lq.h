@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LQ_VERSION 100 /* 0.1.0 */
+#define LQ_VERSION 200 /* 0.2.0 */
 
 typedef void* lq_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
 

@@ -41,7 +41,7 @@ def test_no_torch_types_in_the_abi():
 
 def test_version_and_workspace_arithmetic(pkg):
     lib, L = pkg._lib.lib, pkg._lib
-    assert lib.lq_version() == 100
+    assert lib.lq_version() == 200
     descs = (L.TensorDesc * 3)()
     for d, (o, c, i) in zip(descs, [(256, 512, 512), (784, 128, 1), (0, 4, 4)]):
         d.outer, d.C, d.inner = o, c, i

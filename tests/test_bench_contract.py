@@ -43,6 +43,12 @@ def test_gpu_arm_line():
     assert d["gpu_launches"] == 3 * d["steps"] and d["n_gpus"] == 1 and d["scaling"] == "weak"
     assert d["cpu_baseline"]["kind"] == "port" and 0 < d["cpu_baseline"]["value"] < d["e2e"]["value"]
     assert d["qat"]["unit"] == "images/s" and d["qat"]["value"] > 0 and d["qat"]["e2e"]["h2d_bytes_per_step"] > 0
-    c = d["qat_cifar_paper"]                     # BASELINE configs[1]
+    c = d["qat_cifar_paper"]                     # BASELINE configs[1]: per-channel LEARNED scales, batch 256
     assert "error" not in c and c["config"]["per_gpu_batch"] == 256 and c["value"] > 0
+    assert c["config"]["scale_grad_mode"].startswith("threshold") and d["qat_cifar_paper_ste"]["config"]["scale_grad_mode"].startswith("none")
+    assert d["qat_b128"]["config"]["per_gpu_batch"] == 128 and d["qat_b128"]["value"] > 0            # configs[4] per GPU
+    assert d["qat_custom_loss"]["config"]["workload"].endswith("maxbin") and d["qat_custom_loss"]["value"] > 0   # configs[2]
+    assert d["qat_mnist"]["value"] > 0 and d["mnist_cpu"]["nested"]["value"] > 0                      # configs[0], GPU and CPU
+    assert d["roofline"]["traffic"] is None or "unchanged" in d["roofline"]["traffic_source"]
+    assert 0 < d["e2e"]["frac_of_pcie_bound"] <= 1.2
     assert d["value"] > 3000, "fwd+bwd below half of the HBM roofline: something is wrong with the build"
