@@ -930,16 +930,22 @@ def run_sweep(args):
                 res[tag] = sorted(ts)[len(ts) // 2]
                 del g
             else:
-                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-                for i, (a, b) in enumerate(evs):
-                    a.record(); fn(i % nsets); b.record()
+                # like the headline: `steps` launches between two events (an event record costs ~3 us of stream
+                # time, which a per-launch bracket would charge to every launch); median of five such batches
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                k = 0
+                for a, b in evs:
+                    a.record()
+                    for _ in range(args.steps):
+                        fn(k % nsets); k += 1
+                    b.record()
                 torch.cuda.synchronize()
-                ts = sorted(a.elapsed_time(b) for a, b in evs)
+                ts = sorted(a.elapsed_time(b) / args.steps for a, b in evs)
                 res[tag] = ts[len(ts) // 2]
         gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
         print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "scales": scales, "lambda": lam,
                           "rotating_sets": nsets,
-                          "timing": f"CUDA graph of {args.steps} launches" if graphed else "per-launch CUDA events",
+                          "timing": f"CUDA graph of {args.steps} launches" if graphed else f"{args.steps} launches between two CUDA events, median of 5",
                           "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
                           "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),
                           "fwd_bwd_GBps": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9,

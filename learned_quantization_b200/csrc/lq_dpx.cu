@@ -229,10 +229,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uns
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// (mbar_arrive, bulk_wait_read1: lq_col_tma.cuh)
 
 __global__ void __launch_bounds__(kArThreads, 1) dpx_allreduce_kernel(const __grid_constant__ ArJob job,
                                                                       const __grid_constant__ DpxCtl c) {

@@ -292,6 +292,21 @@ FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, fl
   return f;
 }
 
+// The forward writes no partials, so its COL row chunks need not be the backward's: short-lived blocks (a few trips
+// per thread) leave a finer tail at the end of the grid.  Only the block count changes; vector forms only.
+Geom fwd_geom(long long outer, long long C, long long inner, bool al) {
+  Geom g = make_geom(outer, C, inner, al);
+  if (LQ_COL_FWD_TRIPS > 0 && g.regime == REG_COL && g.vec_ok) {
+    long long rpc = (long long)g.by * LQ_COL_U1 * LQ_COL_FWD_TRIPS;
+    if (rpc < g.rpc) {
+      g.rpc = (int)rpc;
+      g.nchunks = cdiv(g.outer, rpc);
+      g.nblocks = g.nchunks * g.ncolblk;
+    }
+  }
+  return g;
+}
+
 // Internal launch helpers shared with lq_host.cu.
 int fq_fwd_launch(const Geom& g, const float* P, const float* s, float* y, void* codes, int codes_dtype,
                   const QMode& qm, cudaStream_t st) {
@@ -424,7 +439,7 @@ extern "C" int lq_fq_fwd(const float* P, const float* s, float* y, void* codes, 
   QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
   if (rc) return rc;
   const bool al = aligned16(P) && aligned16(y) && (!codes || codes_dtype == LQ_CODES_I8 || aligned16(codes));
-  Geom g = make_geom(outer, C, inner, al);
+  Geom g = fwd_geom(outer, C, inner, al);
   if ((rc = check_blocks(g))) return rc;
   return fq_fwd_launch(g, P, s, y, codes_dtype == LQ_CODES_NONE ? nullptr : codes, codes_dtype, qm, (cudaStream_t)stream);
 }
@@ -555,7 +570,7 @@ extern "C" int lq_mt_fq_fwd(const lq_tensor_desc* descs, int n, int round_mode, 
       if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
       if (d.outer * d.C * d.inner == 0) continue;
       if (!d.P || !d.s || !d.y) { set_error("lq_mt_fq_fwd: desc %d has null P/s/y", i); return LQ_E_NULLPTR; }
-      Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.y));
+      Geom g = fwd_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.y));
       if ((rc = check_blocks(g))) return rc;
       tab.job[tab.n++] = make_job(g, d.P, d.s, nullptr, d.y, nullptr, nullptr, 0, nullptr);
     }

@@ -268,6 +268,128 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
   }
 }
 
+// ---- the same pass as a stream (LQ_STAT_ROLL): the one-unit-per-warp kernels above start every unit with nothing in
+// flight and end it waiting for its last load, so a block spends most of its ~1 us of life on one round trip to HBM and
+// the pass sat at 6.2 TB/s.  Here a tensor gets at most one wave of blocks (4 per SM) and a warp walks units w, w + nw,
+// ...: a register that has been folded is refilled at once from the unit D steps ahead, so eight 16-byte loads per lane
+// stay in flight from the first unit to the last (D = 1, 2, 4 units in flight for segments of <= 1024, 512, 256
+// elements).  Same units, same partial per unit, same order inside a unit: the partials are bit-identical.
+#ifndef LQ_STAT_ROLL
+#define LQ_STAT_ROLL 1
+#endif
+constexpr unsigned kStatRollBlocks = 148 * 4;
+
+template <int KIND, int D>
+__device__ __forceinline__ void stat_row_roll(const Job& j, unsigned blk) {
+  constexpr int UPL = 8 / D;
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)j.nblocks * kWarps;
+  const long long w = (long long)blk * kWarps + (threadIdx.x >> 5);
+  float4 p[D][UPL];
+  int nvec[D];
+  bool fast[D];
+  int redo = 0;
+  auto issue = [&](int d, long long unit) {
+    long long row, grp;
+    int sg;
+    if (j.fast32) {
+      const unsigned r = fd_div((unsigned)unit, j.fd_nseg);
+      sg = (int)((unsigned)unit - r * (unsigned)j.nseg);
+      grp = r - fd_div(r, j.fd_C) * (unsigned)j.C;
+      row = r;
+    } else {
+      row = unit / j.nseg;
+      sg = (int)(unit - row * j.nseg);
+      grp = row % j.C;
+    }
+    const float s = __ldg(j.s + grp);
+    fast[d] = (KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s);
+    const long long base = row * j.inner + (long long)sg * j.seg;
+    const long long rem = j.inner - (long long)sg * j.seg;
+    nvec[d] = (rem < j.seg ? (int)rem : j.seg) >> 2;
+    if (!fast[d]) return;                              // warp-uniform; the unit is re-read by the exact path
+    const float4* P4 = reinterpret_cast<const float4*>(j.P + base);
+#pragma unroll
+    for (int u = 0; u < UPL; ++u) {
+      const int v = u * 32 + lane;
+      if (v < nvec[d]) p[d][u] = j.stream_hint ? __ldcs(P4 + v) : P4[v];
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    nvec[d] = 0; fast[d] = false;
+    const long long unit = w + d * nw;
+    if (unit < j.units) issue(d, unit);
+  }
+  for (long long u0 = w; u0 < j.units; u0 += D * nw) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const long long unit = u0 + d * nw;
+      if (unit < j.units) {                            // warp-uniform
+        float m = -1.f, a = 0.f;
+        bool bad = false;
+        const bool was_fast = fast[d];
+        if (was_fast) {
+#pragma unroll
+          for (int u = 0; u < UPL; ++u) {
+            if (u * 32 + lane < nvec[d]) {
+              const float4 q = p[d][u];
+              if (KIND == LQ_PEN_MAXBIN) {
+                m = fmaxf(fmaxf(m, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
+              } else {
+                const float t = (fabsf(q.x) + fabsf(q.y)) + (fabsf(q.z) + fabsf(q.w));
+                bad |= !(t <= kFastHi);                 // an inf or a NaN among the four
+                a += t;
+              }
+            }
+          }
+        }
+        const long long nxt = unit + D * nw;            // the slot is free: refill it before reducing
+        if (nxt < j.units) issue(d, nxt);
+        if (!was_fast || (KIND == LQ_PEN_DIFFERENCE && __any_sync(0xffffffffu, bad))) {
+          // a scale outside the fast set, or an inf / NaN in the unit: marked (.w = 1) and redone by the exact path after
+          // the stream has drained (a call in here would spill every register that holds a load in flight)
+          if (lane == 0) j.part[unit] = make_float4(0.f, 0.f, 0.f, 1.f);
+          ++redo;
+        } else if (KIND == LQ_PEN_MAXBIN) {
+          // m is -1 or >= 0 and never NaN: as signed integers the bit patterns order like the values
+          m = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(m)));
+          if (lane == 0) j.part[unit] = make_float4(0.f, __uint_as_float(0u), m, 0.f);
+        } else {
+          a = warp_sum(a);
+          if (lane == 0) j.part[unit] = make_float4(a, __uint_as_float(0u), 0.f, 0.f);
+        }
+      }
+    }
+  }
+  if (redo == 0) return;                               // warp-uniform
+  for (long long unit = w; unit < j.units; unit += nw) {
+    float flag = 0.f;
+    if (lane == 0) flag = j.part[unit].w;              // this lane's own store
+    if (__shfl_sync(0xffffffffu, flag, 0) == 1.f) stat_row_generic<KIND>(j, unit);   // writes the unit's partial (.w = 0)
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4) stat_row_roll_kernel(const __grid_constant__ JobTable tab) {
+  int lo = 0, hi = tab.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const Job& j = tab.job[lo];
+  const unsigned blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
+  if (!j.vec || j.seg > 1024) {                        // unaligned or odd-sized rows: the generic traversal, unit by unit
+    const long long nw = (long long)j.nblocks * kWarps;
+    for (long long unit = (long long)blk * kWarps + (threadIdx.x >> 5); unit < j.units; unit += nw) stat_row_generic<KIND>(j, unit);
+    return;
+  }
+  if (j.seg > 512) stat_row_roll<KIND, 1>(j, blk);
+  else if (j.seg > 256) stat_row_roll<KIND, 2>(j, blk);
+  else stat_row_roll<KIND, 4>(j, blk);
+}
+
 template <int KIND>
 __device__ __noinline__ void stat_col_generic(const Job& j, unsigned blk, Acc* smem) {
   typename StatKind<KIND>::Op op;
@@ -314,13 +436,24 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k] = (KIND == LQ_PEN_MAXBIN) ? -1.f : 0.f;
   bool bad = false;
+  // eight rows in flight per thread, refilled one by one (LQ_STAT_ROLL): a register that has been folded is reloaded
+  // at once with the row eight steps further down, so the loads never drain between trips
+  auto ldrow = [&](const float* q) {
+    return j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(q)) : *reinterpret_cast<const float4*>(q);
+  };
+  float4 p[8];
+#if LQ_STAT_ROLL
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (u < rows_mine) p[u] = ldrow(Pp + u * stride);
+#endif
 #pragma unroll 1
   for (int i0 = 0; i0 < rows_blk; i0 += 8) {
-    float4 p[8];
+#if !LQ_STAT_ROLL
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      if (i0 + u < rows_mine) p[u] = j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(Pp + u * stride))
-                                                   : *reinterpret_cast<const float4*>(Pp + u * stride);
+      if (i0 + u < rows_mine) p[u] = ldrow(Pp + u * stride);
+#endif
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (i0 + u < rows_mine) {
@@ -331,6 +464,9 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
           v[0] += fabsf(p[u].x); v[1] += fabsf(p[u].y); v[2] += fabsf(p[u].z); v[3] += fabsf(p[u].w);
         }
       }
+#if LQ_STAT_ROLL
+      if (i0 + 8 + u < rows_mine) p[u] = ldrow(Pp + (8 + u) * stride);
+#endif
     }
     Pp += 8 * stride;
   }
@@ -373,6 +509,27 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
 template <int KIND>
 static int launch_stat(JobTable& tab, cudaStream_t st) {
   JobTable part;
+#if LQ_STAT_ROLL
+  for (int cls = 0; cls < 2; ++cls) {              // 0: ROW (rolling stream), 1: COL (lean, rolling rows)
+    part.n = 0;
+    unsigned total = 0;
+    for (int i = 0; i < tab.n; ++i) {
+      const Job& tj = tab.job[i];
+      if (tj.nblocks == 0 || ((tj.regime == REG_COL) ? 1 : 0) != cls) continue;
+      Job& pj = part.job[part.n];
+      pj = tj;
+      if (cls == 0 && pj.nblocks > kStatRollBlocks) pj.nblocks = kStatRollBlocks;   // one wave; the warps walk the rest
+      pj.block_begin = total;
+      total += pj.nblocks;
+      ++part.n;
+    }
+    if (total == 0) continue;
+    const int rc = (cls == 0)
+        ? launch_after(stat_row_roll_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW launch", part)
+        : launch_after(stat_col_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics COL launch", part);
+    if (rc) return rc;
+  }
+#else
   for (int cls = 0; cls < 3; ++cls) {              // 0: ROW long rows (lean), 1: ROW short rows (generic), 2: COL (lean)
     part.n = 0;
     unsigned total = 0;
@@ -394,6 +551,7 @@ static int launch_stat(JobTable& tab, cudaStream_t st) {
                            "loss-term statistics ROW (short rows) launch", part, typename StatKind<KIND>::Op{});
     if (rc) return rc;
   }
+#endif
   return LQ_OK;
 }
 

@@ -95,6 +95,16 @@ struct LocalIO {
   __device__ __forceinline__ void st_part(float4* p, const float4& v) const { *p = v; }
 };
 
+#ifndef LQ_COL_U1
+#define LQ_COL_U1 8
+#endif
+#ifndef LQ_COL_ORDER
+#define LQ_COL_ORDER 1
+#endif
+// COL forward (no partials, so the row chunk is free): trips of LQ_COL_U1 rows a thread makes; 0 = the backward's chunks
+#ifndef LQ_COL_FWD_TRIPS
+#define LQ_COL_FWD_TRIPS 2
+#endif
 #ifndef LQ_STAT_UNROLL
 #define LQ_STAT_UNROLL 4
 #endif
@@ -217,8 +227,14 @@ __device__ __forceinline__ void run_row(const Job& j, unsigned blk, const Op& op
 template <class Op, bool STREAM, class IO = LocalIO<STREAM>>
 __device__ __forceinline__ void run_col1(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue, const IO& io = IO()) {
   constexpr int U = 8;
+#if LQ_COL_ORDER
+  const long long ncb_ = (j.ncol + j.bx - 1) / j.bx;
+  const long long cb = blk % ncb_;
+  const long long chunk = blk / ncb_;
+#else
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
+#endif
   const int t = threadIdx.x;
   const int ty = t / j.bx;
   const int tx = t - ty * j.bx;
@@ -314,8 +330,14 @@ template <class Op, bool STREAM, bool VEC>
 __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op, Acc* smem, float2* queue) {
   if constexpr (!VEC) { run_col1<Op, STREAM>(j, blk, op, smem, queue); return; }
   constexpr int V = VEC ? 4 : 1;
+#if LQ_COL_ORDER
+  const long long ncb_ = (j.ncol + j.bx - 1) / j.bx;
+  const long long cb = blk % ncb_;
+  const long long chunk = blk / ncb_;
+#else
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
+#endif
   const int t = threadIdx.x;
   const int ty = t / j.bx;
   const int tx = t - ty * j.bx;
@@ -346,7 +368,9 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   // Difference backward), whose per-thread state for four groups would otherwise push the kernel past
   // 64 registers and halve the resident warps.  (The threshold backward does not come here: it takes
   // run_col1 or the TMA-staged kernel.)
-  constexpr int U = (Op::kIn2 && Op::kReduce) ? 2 : 4;
+  // ... and LQ_COL_U1 rows for the one-input operators without a reduction (the forward): ncu had it waiting on loads
+  // (long-scoreboard stall 14 per issue, 70 % DRAM throughput, 35 % issue-active) with four 16-byte loads per thread in flight.
+  constexpr int U = (Op::kIn2 && Op::kReduce) ? 2 : ((!Op::kIn2 && !Op::kReduce) ? LQ_COL_U1 : 4);
   // Addresses: one pointer per array, advanced by a constant stride (the per-row 64-bit multiply of
   // row * W + column and its bound check used to be a third of the instruction stream); rows are
   // counted, not compared: this thread owns rows r0+ty, r0+ty+by, ... (rows_mine of them).
@@ -359,7 +383,7 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
   float* Op_ = out + base;
   // A full trip of four rows hands each of the thread's columns to the operator as one quad (four
   // elements of ONE group: one range guard, one branch), exactly like a ROW thread's 16 bytes.
-  constexpr bool kQuads = (U == 4) && (V == 4) && (Op::kDeferSlots == 0);
+  constexpr bool kQuads = (U % 4 == 0) && (V == 4) && (Op::kDeferSlots == 0);
 
 #pragma unroll 1
   for (int i0 = 0; i0 < rows_blk; i0 += U) {
@@ -380,47 +404,48 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
         }
       }
     }
-    bool done = false;
-    if constexpr (kQuads) {
-      if (i0 + U <= rows_mine) {
-        float o[U][V], c[U][V];
+    // Four rows at a time: a full group of four hands each of the thread's columns to the operator as one quad; the
+    // last 1-3 rows of a chunk, and launches that export codes, take the per-element form (same operations per element,
+    // same accumulation order: the results do not depend on which form ran).
+    constexpr int G = kQuads ? 4 : U;
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          float4 oq, cq;
-          op.quad(make_float4(p[0][k], p[1][k], p[2][k], p[3][k]),
-                  Op::kIn2 ? make_float4(d[0][k], d[1][k], d[2][k], d[3][k]) : make_float4(0.f, 0.f, 0.f, 0.f),
-                  ctx[k], j, acc[k], oq, cq, df);
-          o[0][k] = oq.x; o[1][k] = oq.y; o[2][k] = oq.z; o[3][k] = oq.w;
-          c[0][k] = cq.x; c[1][k] = cq.y; c[2][k] = cq.z; c[3][k] = cq.w;
-        }
+    for (int q0 = 0; q0 < U; q0 += G) {
+      bool done = false;
+      if constexpr (kQuads) {
+        if (i0 + q0 + 4 <= rows_mine && !(Op::kCodes && j.codes)) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (wr) st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(o[u][0], o[u][1], o[u][2], o[u][3]));
-          if (Op::kCodes && j.codes) {
-            const long long e = base + (long long)(i0 + u) * stride;
-#pragma unroll
-            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[u][k]);
+          for (int k = 0; k < V; ++k) {
+            float4 oq, cq;
+            op.quad(make_float4(p[q0][k], p[q0 + 1][k], p[q0 + 2][k], p[q0 + 3][k]),
+                    Op::kIn2 ? make_float4(d[q0][k], d[q0 + 1][k], d[q0 + 2][k], d[q0 + 3][k]) : make_float4(0.f, 0.f, 0.f, 0.f),
+                    ctx[k], j, acc[k], oq, cq, df);
+            p[q0][k] = oq.x; p[q0 + 1][k] = oq.y; p[q0 + 2][k] = oq.z; p[q0 + 3][k] = oq.w;   // outputs take the inputs' registers
           }
-        }
-        done = true;
-      }
-    }
-    if (!done) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (i0 + u < rows_mine) {
-          float o[V], c[V];
-#pragma unroll
-          for (int k = 0; k < V; ++k)
-            op.elem_k(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc, k, o[k], c[k], df);
           if (wr) {
-            if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(o[0], o[1], o[2], o[3]));
-            else st1<STREAM>(Op_ + u * stride, o[0]);
-          }
-          if (Op::kCodes && j.codes) {
-            const long long e = base + (long long)(i0 + u) * stride;
 #pragma unroll
-            for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+            for (int u = q0; u < q0 + 4; ++u)
+              st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(p[u][0], p[u][1], p[u][2], p[u][3]));
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int u = q0; u < q0 + G; ++u) {
+          if (i0 + u < rows_mine) {
+            float o[V], c[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+              op.elem_k(p[u][k], Op::kIn2 ? d[u][k] : 0.f, ctx[k], j, acc, k, o[k], c[k], df);
+            if (wr) {
+              if constexpr (VEC) st4<STREAM>(reinterpret_cast<float4*>(Op_ + u * stride), make_float4(o[0], o[1], o[2], o[3]));
+              else st1<STREAM>(Op_ + u * stride, o[0]);
+            }
+            if (Op::kCodes && j.codes) {
+              const long long e = base + (long long)(i0 + u) * stride;
+#pragma unroll
+              for (int k = 0; k < V; ++k) store_code(j.codes, j.codes_dtype, e + k, c[k]);
+            }
           }
         }
       }
@@ -465,8 +490,11 @@ __device__ __forceinline__ void run_col(const Job& j, unsigned blk, const Op& op
 // COL kernels of the light operators are held to 64 registers (four blocks per SM): grids of ~3.5 blocks
 // per SM (a 4 Mi-element tensor) otherwise need a second wave.  The two-input operators keep
 // what they need (they carry per-thread state for the rare path / four groups).
+#ifndef LQ_COL_FWD_MINBLK
+#define LQ_COL_FWD_MINBLK 3
+#endif
 template <class Op>
-constexpr int kColMinBlocks = Op::kIn2 ? 1 : 4;
+constexpr int kColMinBlocks = Op::kIn2 ? 1 : ((!Op::kReduce) ? LQ_COL_FWD_MINBLK : 4);
 
 template <class Op>
 struct SmemPlan {
