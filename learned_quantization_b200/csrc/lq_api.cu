@@ -96,7 +96,7 @@ extern "C" int lq_workspace_bytes(const lq_tensor_desc* descs, int n, int phase,
     else if (phase == LQ_PHASE_PENALTY_FWD || phase == LQ_PHASE_PENALTY_BWD)
       total += align256((size_t)slots * sizeof(float4)) + align256((size_t)descs[i].C * sizeof(float4));
   }
-  if (phase == LQ_PHASE_PENALTY_FWD || phase == LQ_PHASE_PENALTY_BWD) total += 256;   // scalar slot
+  if (phase == LQ_PHASE_PENALTY_FWD || phase == LQ_PHASE_PENALTY_BWD) total += kPenSlotBytes;   // scalar slot
   *out_bytes = total;
   return LQ_OK;
 }

@@ -197,6 +197,17 @@ template <int KIND> struct StatKind;
 template <> struct StatKind<LQ_PEN_MAXBIN> { using Op = MaxBinStatOp; };
 template <> struct StatKind<LQ_PEN_DIFFERENCE> { using Op = DiffStatOp; };
 
+// ---- the fused epilogue's control words (see "fused epilogue" below).  They live in the workspace's scalar slot
+// (kPenSlotBytes at the end of the workspace: the running total, these counters, the backward's upstream, one term per
+// tensor) and are zeroed by block 0 of every statistics launch of the same call, i.e. before the second stage runs.
+constexpr size_t kPenCtlOff = 16, kPenUpOff = 240, kPenTermOff = 256;     // total: [0, 8); terms: kMaxMT doubles
+enum { kCtlTensors = 0, kCtlPending = 1, kCtlTensor0 = 2, kCtlWords = 2 + kMaxMT };
+static_assert(kPenCtlOff + 4 * kCtlWords <= kPenUpOff && kPenTermOff + 8 * kMaxMT <= kPenSlotBytes, "scalar slot layout");
+
+__device__ __forceinline__ void zero_ctl(unsigned* ctl) {
+  if (ctl && blockIdx.x == 0 && threadIdx.x < kCtlWords) ctl[threadIdx.x] = 0u;
+}
+
 template <int KIND>
 __device__ __noinline__ void stat_row_generic(const Job& j, long long unit) {
   typename StatKind<KIND>::Op op;
@@ -206,7 +217,7 @@ __device__ __noinline__ void stat_row_generic(const Job& j, long long unit) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_constant__ JobTable tab) {
+__global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_constant__ JobTable tab, unsigned* ctl) {
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -215,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
   cudaGridDependencySynchronize();
+  zero_ctl(ctl);
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blk * kWarps + (threadIdx.x >> 5);
   if (unit >= j.units) return;
@@ -268,110 +280,12 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
   }
 }
 
-// ---- the same pass as a stream (LQ_STAT_ROLL): the one-unit-per-warp kernels above start every unit with nothing in
-// flight and end it waiting for its last load, so a block spends most of its ~1 us of life on one round trip to HBM and
-// the pass sat at 6.2 TB/s.  Here a tensor gets at most one wave of blocks (4 per SM) and a warp walks units w, w + nw,
-// ...: a register that has been folded is refilled at once from the unit D steps ahead, so eight 16-byte loads per lane
-// stay in flight from the first unit to the last (D = 1, 2, 4 units in flight for segments of <= 1024, 512, 256
-// elements).  Same units, same partial per unit, same order inside a unit: the partials are bit-identical.
-#ifndef LQ_STAT_ROLL
-#define LQ_STAT_ROLL 1
-#endif
-constexpr unsigned kStatRollBlocks = 148 * 4;
-
-template <int KIND, int D>
-__device__ __forceinline__ void stat_row_roll(const Job& j, unsigned blk) {
-  constexpr int UPL = 8 / D;
-  const int lane = threadIdx.x & 31;
-  const long long nw = (long long)j.nblocks * kWarps;
-  const long long w = (long long)blk * kWarps + (threadIdx.x >> 5);
-  float4 p[D][UPL];
-  int nvec[D];
-  bool fast[D];
-  int redo = 0;
-  auto issue = [&](int d, long long unit) {
-    long long row, grp;
-    int sg;
-    if (j.fast32) {
-      const unsigned r = fd_div((unsigned)unit, j.fd_nseg);
-      sg = (int)((unsigned)unit - r * (unsigned)j.nseg);
-      grp = r - fd_div(r, j.fd_C) * (unsigned)j.C;
-      row = r;
-    } else {
-      row = unit / j.nseg;
-      sg = (int)(unit - row * j.nseg);
-      grp = row % j.C;
-    }
-    const float s = __ldg(j.s + grp);
-    fast[d] = (KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s);
-    const long long base = row * j.inner + (long long)sg * j.seg;
-    const long long rem = j.inner - (long long)sg * j.seg;
-    nvec[d] = (rem < j.seg ? (int)rem : j.seg) >> 2;
-    if (!fast[d]) return;                              // warp-uniform; the unit is re-read by the exact path
-    const float4* P4 = reinterpret_cast<const float4*>(j.P + base);
-#pragma unroll
-    for (int u = 0; u < UPL; ++u) {
-      const int v = u * 32 + lane;
-      if (v < nvec[d]) p[d][u] = j.stream_hint ? __ldcs(P4 + v) : P4[v];
-    }
-  };
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    nvec[d] = 0; fast[d] = false;
-    const long long unit = w + d * nw;
-    if (unit < j.units) issue(d, unit);
-  }
-  for (long long u0 = w; u0 < j.units; u0 += D * nw) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const long long unit = u0 + d * nw;
-      if (unit < j.units) {                            // warp-uniform
-        float m = -1.f, a = 0.f;
-        bool bad = false;
-        const bool was_fast = fast[d];
-        if (was_fast) {
-#pragma unroll
-          for (int u = 0; u < UPL; ++u) {
-            if (u * 32 + lane < nvec[d]) {
-              const float4 q = p[d][u];
-              if (KIND == LQ_PEN_MAXBIN) {
-                m = fmaxf(fmaxf(m, fabsf(q.x)), fmaxf(fabsf(q.y), fmaxf(fabsf(q.z), fabsf(q.w))));
-              } else {
-                const float t = (fabsf(q.x) + fabsf(q.y)) + (fabsf(q.z) + fabsf(q.w));
-                bad |= !(t <= kFastHi);                 // an inf or a NaN among the four
-                a += t;
-              }
-            }
-          }
-        }
-        const long long nxt = unit + D * nw;            // the slot is free: refill it before reducing
-        if (nxt < j.units) issue(d, nxt);
-        if (!was_fast || (KIND == LQ_PEN_DIFFERENCE && __any_sync(0xffffffffu, bad))) {
-          // a scale outside the fast set, or an inf / NaN in the unit: marked (.w = 1) and redone by the exact path after
-          // the stream has drained (a call in here would spill every register that holds a load in flight)
-          if (lane == 0) j.part[unit] = make_float4(0.f, 0.f, 0.f, 1.f);
-          ++redo;
-        } else if (KIND == LQ_PEN_MAXBIN) {
-          // m is -1 or >= 0 and never NaN: as signed integers the bit patterns order like the values
-          m = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(m)));
-          if (lane == 0) j.part[unit] = make_float4(0.f, __uint_as_float(0u), m, 0.f);
-        } else {
-          a = warp_sum(a);
-          if (lane == 0) j.part[unit] = make_float4(a, __uint_as_float(0u), 0.f, 0.f);
-        }
-      }
-    }
-  }
-  if (redo == 0) return;                               // warp-uniform
-  for (long long unit = w; unit < j.units; unit += nw) {
-    float flag = 0.f;
-    if (lane == 0) flag = j.part[unit].w;              // this lane's own store
-    if (__shfl_sync(0xffffffffu, flag, 0) == 1.f) stat_row_generic<KIND>(j, unit);   // writes the unit's partial (.w = 0)
-  }
-}
-
+// Short rows (segments below 1024 elements: four loads per lane already cover the row): the generic ROW traversal,
+// eight blocks per SM (letting a warp of the lean kernel take two 512-element rows was slower: 60 us against 47).
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 4) stat_row_roll_kernel(const __grid_constant__ JobTable tab) {
+__global__ void __launch_bounds__(kThreads, LQ_STAT_MINBLK) stat_short_kernel(const __grid_constant__ JobTable tab, unsigned* ctl) {
+  using Op = typename StatKind<KIND>::Op;
+  __shared__ float2 queue[1];
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -380,14 +294,10 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_roll_kernel(const __grid
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
   cudaGridDependencySynchronize();
-  if (!j.vec || j.seg > 1024) {                        // unaligned or odd-sized rows: the generic traversal, unit by unit
-    const long long nw = (long long)j.nblocks * kWarps;
-    for (long long unit = (long long)blk * kWarps + (threadIdx.x >> 5); unit < j.units; unit += nw) stat_row_generic<KIND>(j, unit);
-    return;
-  }
-  if (j.seg > 512) stat_row_roll<KIND, 1>(j, blk);
-  else if (j.seg > 256) stat_row_roll<KIND, 2>(j, blk);
-  else stat_row_roll<KIND, 4>(j, blk);
+  zero_ctl(ctl);
+  Op op;
+  if (j.vec) run_row<Op, false, true>(j, blk, op, queue);
+  else run_row<Op, false, false>(j, blk, op, queue);
 }
 
 template <int KIND>
@@ -399,7 +309,7 @@ __device__ __noinline__ void stat_col_generic(const Job& j, unsigned blk, Acc* s
 
 // COL: a thread owns four adjacent columns (one 16-byte load per row) and walks down its rows, eight rows in flight.
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_constant__ JobTable tab) {
+__global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_constant__ JobTable tab, unsigned* ctl) {
   __shared__ Acc smem[4 * kThreads];
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
@@ -409,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
   const Job& j = tab.job[lo];
   const unsigned blk = blockIdx.x - j.block_begin;
   cudaGridDependencySynchronize();
+  zero_ctl(ctl);
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
   const int t = threadIdx.x;
@@ -436,24 +347,13 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k] = (KIND == LQ_PEN_MAXBIN) ? -1.f : 0.f;
   bool bad = false;
-  // eight rows in flight per thread, refilled one by one (LQ_STAT_ROLL): a register that has been folded is reloaded
-  // at once with the row eight steps further down, so the loads never drain between trips
-  auto ldrow = [&](const float* q) {
-    return j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(q)) : *reinterpret_cast<const float4*>(q);
-  };
-  float4 p[8];
-#if LQ_STAT_ROLL
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    if (u < rows_mine) p[u] = ldrow(Pp + u * stride);
-#endif
 #pragma unroll 1
   for (int i0 = 0; i0 < rows_blk; i0 += 8) {
-#if !LQ_STAT_ROLL
+    float4 p[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      if (i0 + u < rows_mine) p[u] = ldrow(Pp + u * stride);
-#endif
+      if (i0 + u < rows_mine) p[u] = j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(Pp + u * stride))
+                                                   : *reinterpret_cast<const float4*>(Pp + u * stride);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (i0 + u < rows_mine) {
@@ -464,9 +364,6 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
           v[0] += fabsf(p[u].x); v[1] += fabsf(p[u].y); v[2] += fabsf(p[u].z); v[3] += fabsf(p[u].w);
         }
       }
-#if LQ_STAT_ROLL
-      if (i0 + 8 + u < rows_mine) p[u] = ldrow(Pp + (8 + u) * stride);
-#endif
     }
     Pp += 8 * stride;
   }
@@ -507,29 +404,8 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
 // (6.5 TB/s); shorter rows -> the generic ROW traversal, whose four loads per lane already cover the whole row (letting
 // a warp take two 512-element rows was slower: 60 us against 47); interleaved layouts -> the lean COL kernel.
 template <int KIND>
-static int launch_stat(JobTable& tab, cudaStream_t st) {
+static int launch_stat(JobTable& tab, cudaStream_t st, unsigned* ctl) {
   JobTable part;
-#if LQ_STAT_ROLL
-  for (int cls = 0; cls < 2; ++cls) {              // 0: ROW (rolling stream), 1: COL (lean, rolling rows)
-    part.n = 0;
-    unsigned total = 0;
-    for (int i = 0; i < tab.n; ++i) {
-      const Job& tj = tab.job[i];
-      if (tj.nblocks == 0 || ((tj.regime == REG_COL) ? 1 : 0) != cls) continue;
-      Job& pj = part.job[part.n];
-      pj = tj;
-      if (cls == 0 && pj.nblocks > kStatRollBlocks) pj.nblocks = kStatRollBlocks;   // one wave; the warps walk the rest
-      pj.block_begin = total;
-      total += pj.nblocks;
-      ++part.n;
-    }
-    if (total == 0) continue;
-    const int rc = (cls == 0)
-        ? launch_after(stat_row_roll_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW launch", part)
-        : launch_after(stat_col_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics COL launch", part);
-    if (rc) return rc;
-  }
-#else
   for (int cls = 0; cls < 3; ++cls) {              // 0: ROW long rows (lean), 1: ROW short rows (generic), 2: COL (lean)
     part.n = 0;
     unsigned total = 0;
@@ -545,14 +421,119 @@ static int launch_stat(JobTable& tab, cudaStream_t st) {
     }
     if (total == 0) continue;
     int rc;
-    if (cls == 0) rc = launch_after(stat_row_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW launch", part);
-    else if (cls == 2) rc = launch_after(stat_col_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics COL launch", part);
-    else rc = launch_after(mt_kernel<typename StatKind<KIND>::Op, REG_ROW>, dim3(total), dim3(kThreads), st,
-                           "loss-term statistics ROW (short rows) launch", part, typename StatKind<KIND>::Op{});
+    if (cls == 0) rc = launch_after(stat_row_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW launch", part, ctl);
+    else if (cls == 2) rc = launch_after(stat_col_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics COL launch", part, ctl);
+    else rc = launch_after(stat_short_kernel<KIND>, dim3(total), dim3(kThreads), st, "loss-term statistics ROW (short rows) launch", part, ctl);
     if (rc) return rc;
   }
-#endif
   return LQ_OK;
+}
+
+// Per-tensor scalar stage: penalty = sum_t mean_t * dim_t / normalizer (LF:110-116 etc.)
+struct ScalarJob { const float4* gstat; const float* s; long long C; double n; };
+struct ScalarTable { int n, kind, first, last; double normalizer; ScalarJob job[kMaxMT]; };
+
+__device__ __forceinline__ double gstat_double(const float4& v) {
+  const unsigned long long bits = (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32);
+  return __longlong_as_double((long long)bits);
+}
+
+__device__ __forceinline__ double scalar_group_value(int kind, const ScalarJob& j, long long g) {
+  if (kind == LQ_PEN_MAXBIN) return (double)__ldcg(&j.gstat[g].x);          // written by other blocks of this launch:
+  if (kind == LQ_PEN_DIFFERENCE) return gstat_double(__ldcg(&j.gstat[g]));    // read past L1
+  const float sv = j.s[g];
+  const float nz = (sv == 0.0f) ? kEps : sv;     // LF:255-256
+  return (double)__fdiv_rn(1.0f, nz);            // LF:258
+}
+// mean over groups (MaxBin LF:110, Inverse LF:258) or over elements (Difference LF:178), times #P
+__device__ __forceinline__ double scalar_term(int kind, const ScalarJob& j, double v) {
+  const double denom = (kind == LQ_PEN_DIFFERENCE) ? j.n : (double)j.C;
+  const float mean = (float)(v / denom);
+  return (double)__fmul_rn(mean, (float)j.n);
+}
+__device__ __forceinline__ void scalar_finish(const ScalarTable& tab, const double* term, double* total, float* out) {
+  double acc = tab.first ? 0.0 : *total;
+  for (int t = 0; t < tab.n; ++t) acc += term[t];              // tensor order
+  *total = acc;
+  if (tab.last) *out = (float)(acc / tab.normalizer);
+}
+
+// Stand-alone form (Inverse, which has no element pass): warp w takes tensors w, w+8, ...: the per-tensor term needs one
+// warp reduction, the terms are then added in tensor order by one thread (a single block used to walk the tensors one
+// after the other with two block barriers each: 30 us for the 40 tensors of the IMAGENETTE model).
+__global__ void __launch_bounds__(256) pen_scalar_kernel(const __grid_constant__ ScalarTable tab, double* total, float* out) {
+  cudaGridDependencySynchronize();
+  __shared__ double term[kMaxMT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < tab.n; t += 8) {
+    const ScalarJob& j = tab.job[t];
+    double v = 0.0;
+    for (long long g = lane; g < j.C; g += 32) v += scalar_group_value(tab.kind, j, g);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) term[t] = scalar_term(tab.kind, j, v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) scalar_finish(tab, term, total, out);
+}
+
+// ---- fused epilogue (LQ_PEN_FUSED).  MaxBin / Difference used to end in up to three small dependent launches after the
+// second stage (pending ties, scalar stage), each a drain and a ramp of the whole GPU; the scalar stage walked the tensors
+// with one warp each.  Now the second-stage blocks of a tensor count themselves off (ctl[kCtlTensor0 + t]); the LAST block
+// of tensor t -- all its groups' statistics are then in memory -- reduces them to the tensor's term with the whole block
+// (thread i folds groups i, i + 128, ... in order, then a fixed tree: deterministic whichever block comes last), and the
+// last tensor to finish adds the terms in tensor order.  The forward VALUE does not depend on the tie counts, so it is
+// complete when the second stage ends; the tail kernel (MaxBin) only serves groups whose ties were left pending and
+// returns at once when there are none (ctl[kCtlPending]).
+#ifndef LQ_PEN_FUSED
+#define LQ_PEN_FUSED 1
+#endif
+
+// true in every thread of the block that arrives last on *counter (of `expected` blocks)
+__device__ __forceinline__ bool last_block(unsigned* counter, unsigned expected) {
+  __shared__ unsigned ticket;
+  __syncthreads();                                        // the block's own writes are done
+  if (threadIdx.x == 0) { __threadfence(); ticket = atomicAdd(counter, 1u); }
+  __syncthreads();
+  const bool last = ticket == expected - 1u;
+  if (last) __threadfence();
+  return last;
+}
+
+// called by every second-stage block of tensor t (kFinThreads threads) after its group is final
+__device__ __forceinline__ void pen_fused_epilogue(const ScalarTable& sc, int t, unsigned* ctl, double* term, double* total, float* out) {
+  const ScalarJob& j = sc.job[t];
+  if (!last_block(&ctl[kCtlTensor0 + t], (unsigned)j.C)) return;
+  double v = 0.0;
+  for (long long g0 = threadIdx.x; g0 < j.C; g0 += 4 * kFinThreads) {       // four loads in flight
+    double x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long g = g0 + (long long)u * kFinThreads;
+      x[u] = (g < j.C) ? scalar_group_value(sc.kind, j, g) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v += x[u];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ double wsum[kFinThreads / 32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    v = wsum[0];
+#pragma unroll
+    for (int i = 1; i < kFinThreads / 32; ++i) v += wsum[i];
+    term[t] = scalar_term(sc.kind, j, v);
+    __threadfence();
+    if (atomicAdd(&ctl[kCtlTensors], 1u) == (unsigned)sc.n - 1u) {          // every tensor's term is in memory
+      __threadfence();
+      double acc = sc.first ? 0.0 : *total;
+      for (int i = 0; i < sc.n; ++i) acc += __ldcg(&term[i]);
+      *total = acc;
+      if (sc.last) *out = (float)(acc / sc.normalizer);
+    }
+  }
 }
 
 // --------------------------------------------------------------- second stages
@@ -625,7 +606,7 @@ __device__ __forceinline__ long long partial_index1(const FinJob& f, long long g
   return ch * f.W + g * f.inner + ci;
 }
 
-__device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb) {
+__device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb, unsigned* ctl) {
   __shared__ long long list[kTieList];
   __shared__ int nlist, nlin_list;
   __shared__ unsigned total;
@@ -670,7 +651,7 @@ __device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb)
     if (nlist > kTieList) overflow = true;
   }
   if (overflow) {                               // block-uniform: mark the group pending (.z = 1) for pen_ties_kernel
-    if (threadIdx.x == 0) f.gstat[g].z = 1.f;
+    if (threadIdx.x == 0) { f.gstat[g].z = 1.f; if (ctl) atomicAdd(&ctl[kCtlPending], 1u); }
     return;
   }
   const float sc = all ? f.s[g] : 1.f;
@@ -698,7 +679,7 @@ __device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb)
   if (threadIdx.x == 0) f.gstat[g].y = __uint_as_float(total);
 }
 
-__device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g) {
+__device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g, unsigned* ctl) {
   const long long K = partials_per_group(f);
   double sum = 0.0, sum_c = 0.0;
   float mx = -1.f;
@@ -797,10 +778,12 @@ __device__ __forceinline__ void pen_finalize_group(const FinJob& f, long long g)
   __syncthreads();
   const float lo = tie_lo, mb = tie_mb;
   if (lo == -1.f) return;                      // exact regime / nothing but NaNs: already final
-  pen_count_ties(f, g, lo, mb);
+  pen_count_ties(f, g, lo, mb, ctl);
 }
 
-__global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_constant__ FinTable tab) {
+__global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_constant__ FinTable tab,
+                                                                   const __grid_constant__ ScalarTable sc, unsigned* ctl,
+                                                                   double* term, double* total, float* out) {
   int lo = 0, hi = tab.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -808,7 +791,8 @@ __global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_
   }
   const FinJob& f = tab.job[lo];
   cudaGridDependencySynchronize();
-  pen_finalize_group(f, blockIdx.x - f.group_begin);
+  pen_finalize_group(f, blockIdx.x - f.group_begin, ctl);
+  if (ctl) pen_fused_epilogue(sc, lo, ctl, term, total, out);     // (null: the backward's second stage, or the unfused chain)
 }
 
 // The groups pen_count_ties left pending (gstat.z == 1: more candidate units than its list holds -- many equal
@@ -817,7 +801,12 @@ __global__ void __launch_bounds__(kFinThreads) pen_finalize_kernel(const __grid_
 struct TieTable { int n; unsigned begin[kMaxMT]; };
 constexpr unsigned kTieBlocksPerTensor = 64;
 
-__global__ void __launch_bounds__(256) pen_ties_kernel(const __grid_constant__ JobTable tab, const __grid_constant__ TieTable tt) {
+__global__ void __launch_bounds__(256) pen_ties_kernel(const __grid_constant__ JobTable tab, const __grid_constant__ TieTable tt,
+                                                       const unsigned* ctl) {
+  if (ctl) {
+    cudaGridDependencySynchronize();
+    if (ctl[kCtlPending] == 0u) return;                   // the usual case: the second stage has counted every group's ties
+  }
   int lo_i = 0, hi_i = tt.n - 1;
   while (lo_i < hi_i) {
     const int mid = (lo_i + hi_i + 1) >> 1;
@@ -863,52 +852,6 @@ __global__ void __launch_bounds__(256) pen_ties_kernel(const __grid_constant__ J
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned*>(&gstat[ug].y), cnt);
     }
-  }
-}
-
-// Per-tensor scalar stage: penalty = sum_t mean_t * dim_t / normalizer (LF:110-116 etc.)
-struct ScalarJob { const float4* gstat; const float* s; long long C; double n; };
-struct ScalarTable { int n, kind, first, last; double normalizer; ScalarJob job[kMaxMT]; };
-
-__device__ __forceinline__ double gstat_double(const float4& v) {
-  const unsigned long long bits = (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32);
-  return __longlong_as_double((long long)bits);
-}
-
-// Warp w takes tensors w, w+8, ...: the per-tensor term needs one warp reduction, the terms are then
-// added in tensor order by one thread (a single block used to walk the tensors one after the other
-// with two block barriers each: 30 us for the 40 tensors of the IMAGENETTE model).
-__global__ void __launch_bounds__(256) pen_scalar_kernel(const __grid_constant__ ScalarTable tab, double* total, float* out) {
-  cudaGridDependencySynchronize();
-  __shared__ double term[kMaxMT];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t = warp; t < tab.n; t += 8) {
-    const ScalarJob& j = tab.job[t];
-    double v = 0.0;
-    for (long long g = lane; g < j.C; g += 32) {
-      if (tab.kind == LQ_PEN_MAXBIN) v += (double)j.gstat[g].x;
-      else if (tab.kind == LQ_PEN_DIFFERENCE) v += gstat_double(j.gstat[g]);
-      else {
-        const float sv = j.s[g];
-        const float nz = (sv == 0.0f) ? kEps : sv;     // LF:255-256
-        v += (double)__fdiv_rn(1.0f, nz);              // LF:258
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) {
-      // mean over groups (MaxBin LF:110, Inverse LF:258) or over elements (Difference LF:178), times #P
-      const double denom = (tab.kind == LQ_PEN_DIFFERENCE) ? j.n : (double)j.C;
-      const float mean = (float)(v / denom);
-      term[t] = (double)__fmul_rn(mean, (float)j.n);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double acc = tab.first ? 0.0 : *total;
-    for (int t = 0; t < tab.n; ++t) acc += term[t];
-    *total = acc;
-    if (tab.last) *out = (float)(acc / tab.normalizer);
   }
 }
 
@@ -1009,7 +952,7 @@ static size_t pen_layout(const lq_tensor_desc* descs, int n, PenLayout* lay) {
     lay[i].gstat_off = off;
     off += align256((size_t)descs[i].C * sizeof(float4));
   }
-  return off;   // scalar slot (256 B) follows
+  return off;   // scalar slot (kPenSlotBytes) follows
 }
 
 static int pen_check(const char* who, int kind, const lq_tensor_desc* descs, int n, void* ws, size_t ws_bytes,
@@ -1027,13 +970,13 @@ static int pen_check(const char* who, int kind, const lq_tensor_desc* descs, int
   }
   if (nrm == 0.0) { set_error("%s: all tensors are empty", who); return LQ_E_BADSHAPE; }
   PenLayout* lay = new PenLayout[n];
-  const size_t need = pen_layout(descs, n, lay) + 256;
+  const size_t need = pen_layout(descs, n, lay) + kPenSlotBytes;
   if (!ws || ws_bytes < need || !aligned16(ws)) {
     delete[] lay;
     set_error("%s: workspace %zu B (16-B aligned) needed, got %zu", who, need, ws_bytes);
     return LQ_E_WORKSPACE;
   }
-  *lay_out = lay; *scalar_off = need - 256; *normalizer = nrm;
+  *lay_out = lay; *scalar_off = need - kPenSlotBytes; *normalizer = nrm;
   return LQ_OK;
 }
 
@@ -1084,14 +1027,20 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
       sc.job[sc.n++] = ScalarJob{gstat, d.s, d.C, (double)cnt};
     }
     if (rc) break;
+    unsigned* ctl = LQ_PEN_FUSED ? reinterpret_cast<unsigned*>(base + soff + kPenCtlOff) : nullptr;
+    double* term = reinterpret_cast<double*>(base + soff + kPenTermOff);
     if (tab.n) {
-      if (kind == LQ_PEN_MAXBIN) rc = launch_stat<LQ_PEN_MAXBIN>(tab, st);
-      else rc = launch_stat<LQ_PEN_DIFFERENCE>(tab, st);
+      if (kind == LQ_PEN_MAXBIN) rc = launch_stat<LQ_PEN_MAXBIN>(tab, st, ctl);
+      else rc = launch_stat<LQ_PEN_DIFFERENCE>(tab, st, ctl);
       if (rc) break;
       if ((rc = pen_fold_large(fin, st))) break;
-      if ((rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty finalize launch", fin))) break;
+      // second stage; with the fused epilogue its last blocks also produce the per-tensor terms and the penalty
+      if ((rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty finalize launch", fin, sc, ctl,
+                             term, total, out_penalty))) break;
       if (kind == LQ_PEN_MAXBIN && tie_blocks &&
-          (rc = launch_after(pen_ties_kernel, dim3(tie_blocks), dim3(256), st, "penalty tie launch", tab, ties))) break;
+          (rc = launch_after(pen_ties_kernel, dim3(tie_blocks), dim3(256), st, "penalty tie launch", tab, ties,
+                             (const unsigned*)ctl))) break;
+      if (ctl) continue;
     }
     rc = launch_after(pen_scalar_kernel, dim3(1), dim3(256), st, "penalty scalar launch", sc, total, out_penalty);
   }
@@ -1107,7 +1056,7 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
   cudaStream_t st = (cudaStream_t)stream;
   char* base = static_cast<char*>(ws);
   const float g_total = 1.0f / (float)nrm;                     // LF:116 / LF:195 / LF:275 (times *up on device)
-  float* up = reinterpret_cast<float*>(base + soff + 128);
+  float* up = reinterpret_cast<float*>(base + soff + kPenUpOff);
   upstream_kernel<<<1, 1, 0, st>>>(up, upstream, upstream_dev);
   rc = cuda_fail(cudaGetLastError(), "upstream launch");
   int accum = -1;
@@ -1170,7 +1119,8 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
       if (rc) break;
       if (fin.n) {
         if ((rc = pen_fold_large(fin, st))) break;
-        rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty ds finalize launch", fin);
+        rc = launch_after(pen_finalize_kernel, dim3(groups), dim3(kFinThreads), st, "penalty ds finalize launch", fin,
+                          ScalarTable{}, (unsigned*)nullptr, (double*)nullptr, (double*)nullptr, (float*)nullptr);
       }
     }
   }
