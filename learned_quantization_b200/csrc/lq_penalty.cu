@@ -320,8 +320,14 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
   const unsigned blk = blockIdx.x - j.block_begin;
   cudaGridDependencySynchronize();
   zero_ctl(ctl);
+#if LQ_COL_ORDER
+  const long long ncb_ = (j.ncol + j.bx - 1) / j.bx;     // column blocks of the same rows are neighbours in launch order
+  const long long cb = blk % ncb_;
+  const long long chunk = blk / ncb_;
+#else
   const long long chunk = blk % j.nchunks;
   const long long cb = blk / j.nchunks;
+#endif
   const int t = threadIdx.x;
   const int ty = t / j.bx;
   const int tx = t - ty * j.bx;
@@ -664,13 +670,27 @@ __device__ void pen_count_ties(const FinJob& f, long long g, float lo, float mb,
       const long long base = (o * f.C + g) * f.inner + sg * f.seg;
       const long long rem = f.inner - sg * f.seg;
       const int len = rem < f.seg ? (int)rem : f.seg;
-      for (int e = threadIdx.x; e < len; e += kFinThreads) cnt += tie_hit(f.P[base + e], lo, mb, sc);
+      // all of the unit's loads in flight at once (the tensor has been streamed through: these come from HBM, and one
+      // load per trip made this the longest step of the second stage)
+      for (int e0 = threadIdx.x; e0 < len; e0 += 8 * kFinThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + u * kFinThreads; v[u] = (e < len) ? f.P[base + e] : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (e0 + u * kFinThreads < len) cnt += tie_hit(v[u], lo, mb, sc);
+      }
     } else {
       const long long ch = k / f.inner, ci = k - ch * f.inner;
       const long long col = g * f.inner + ci;
       const long long r0 = ch * f.rpc;
       const long long r1 = (r0 + f.rpc < f.outer) ? r0 + f.rpc : f.outer;
-      for (long long r = r0 + threadIdx.x; r < r1; r += kFinThreads) cnt += tie_hit(f.P[r * f.W + col], lo, mb, sc);
+      for (long long q0 = r0 + threadIdx.x; q0 < r1; q0 += 8 * kFinThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long long r = q0 + u * kFinThreads; v[u] = (r < r1) ? f.P[r * f.W + col] : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (q0 + u * kFinThreads < r1) cnt += tie_hit(v[u], lo, mb, sc);
+      }
     }
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -853,6 +873,257 @@ __global__ void __launch_bounds__(256) pen_ties_kernel(const __grid_constant__ J
       if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned*>(&gstat[ug].y), cnt);
     }
   }
+}
+
+// --------------------------------------------------------------- lean backward kernel, interleaved layouts
+// The generic COL traversal carries a full operator context per column (reciprocal, operands, three constants: ten
+// registers times four columns) and ran the Difference backward at 4.8 TB/s on [131072, 512] (64 registers, spilling).
+// In the fast regime the element gradient needs one constant per column (Difference: g_P = sign(P) * (sigma * k1);
+// MaxBin: two, the threshold |P| >= lo and coef / s), so this kernel keeps eight rows in flight per thread like the
+// forward statistics, on the same geometry (LONG row chunks: the Difference partials shrink from 6 % of the traffic to
+// under 1 %, and forward and backward cut the tensor into the same quads, so they agree on which elements are "ordinary").
+// Quads that are not ordinary (an inf / NaN / huge value among four rows of a column) take the exact per-element form
+// and accumulate into the column's partial exactly as the generic traversal does; blocks whose scales are outside the
+// fast set go to the generic traversal, out of line.
+template <int KIND, bool ACCUM> struct BwdKind;
+template <bool ACCUM> struct BwdKind<LQ_PEN_MAXBIN, ACCUM> { using Op = MaxBinBwdOp<ACCUM>; };
+template <bool ACCUM> struct BwdKind<LQ_PEN_DIFFERENCE, ACCUM> { using Op = DiffBwdOp<ACCUM>; };
+
+// Difference, lean kernel below: up to four rows of a thread's four columns that are NOT all ordinary (an inf / NaN /
+// huge value in a quad), or the last 1-3 rows of a chunk -- re-read from memory and processed exactly as
+// DiffBwdOp::quad (full = four rows: the quad's split) / ::elem (per element) do.  Returns the four columns' terms of
+// the scale gradient.  Rare and out of line, so that the streaming loop keeps its registers.
+template <bool ACCUM>
+__device__ __noinline__ float4 diff_bwd_rows_slow(const Job& j, const float* Pp, float* Xp, long long stride, int nrows,
+                                                  long long col0, float gabs) {
+  float accv[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool full = nrows == 4;
+  for (int k = 0; k < 4; ++k) {
+    const float s = __ldg(j.s + (col0 + k) / j.inner);
+    const float k1 = __fadd_rn(gabs, __fdiv_rn(-gabs, s));
+    const float sigma = diff_fast_scale(s) ? (s <= 0.5f ? -1.f : 1.f) : 0.f;
+    float pv[4];
+    for (int u = 0; u < 4; ++u) pv[u] = (u < nrows) ? Pp[u * stride + k] : 0.f;
+    const float tq = (fabsf(pv[0]) + fabsf(pv[1])) + (fabsf(pv[2]) + fabsf(pv[3]));
+    for (int u = 0; u < nrows; ++u) {
+      const bool ord = sigma != 0.f && (full ? (tq <= kFastHi) : (fabsf(pv[u]) <= kFastHi));
+      float g;
+      if (ord) {
+        g = __fmul_rn(__fmul_rn(sigma, sgn(pv[u])), k1);
+      } else {
+        const float pq = __fdiv_rn(pv[u], s);
+        const float sg = sgn(__fsub_rn(pv[u], pq));
+        g = __fmul_rn(sg, k1);
+        accv[k] += __fmul_rn(__fmul_rn(-sg, gabs), __fdiv_rn(-pq, s));
+      }
+      float* x = Xp + u * stride + k;
+      *x = ACCUM ? __fadd_rn(*x, g) : g;
+    }
+  }
+  return make_float4(accv[0], accv[1], accv[2], accv[3]);
+}
+
+// four rows x four columns: is every column's quad ordinary (DiffBwdOp::quad's test, all four at once)?
+__device__ __forceinline__ bool diff_quads_ordinary(const float4& a, const float4& b, const float4& c, const float4& d) {
+  const float t0 = (fabsf(a.x) + fabsf(b.x)) + (fabsf(c.x) + fabsf(d.x));
+  const float t1 = (fabsf(a.y) + fabsf(b.y)) + (fabsf(c.y) + fabsf(d.y));
+  const float t2 = (fabsf(a.z) + fabsf(b.z)) + (fabsf(c.z) + fabsf(d.z));
+  const float t3 = (fabsf(a.w) + fabsf(b.w)) + (fabsf(c.w) + fabsf(d.w));
+  return t0 <= kFastHi && t1 <= kFastHi && t2 <= kFastHi && t3 <= kFastHi;      // a NaN fails its compare
+}
+
+template <int KIND, bool ACCUM>
+__device__ __noinline__ void pen_bwd_col_generic(const Job& j, unsigned blk, Acc* smem, const float* up) {
+  using Op = typename BwdKind<KIND, ACCUM>::Op;
+  Op op; op.up = up;
+  if (j.vec) run_col<Op, false, true>(j, blk, op, smem, nullptr);
+  else run_col<Op, false, false>(j, blk, op, smem, nullptr);
+}
+
+#ifndef LQ_PENB_MINBLK
+#define LQ_PENB_MINBLK 3
+#endif
+template <int KIND, bool ACCUM>
+__global__ void __launch_bounds__(kThreads, LQ_PENB_MINBLK) pen_bwd_col_kernel(const __grid_constant__ JobTable tab, const float* up) {
+  constexpr bool kDiff = KIND == LQ_PEN_DIFFERENCE;
+  constexpr int U = ACCUM ? 4 : 8;                  // rows in flight per thread (two arrays when accumulating)
+  __shared__ Acc smem[kDiff ? 4 * kThreads : 1];
+  int lo_i = 0, hi_i = tab.n - 1;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (tab.job[mid].block_begin <= blockIdx.x) lo_i = mid; else hi_i = mid - 1;
+  }
+  const Job& j = tab.job[lo_i];
+  const unsigned blk = blockIdx.x - j.block_begin;
+  cudaGridDependencySynchronize();
+#if LQ_COL_ORDER
+  const long long ncb_ = (j.ncol + j.bx - 1) / j.bx;
+  const long long cb = blk % ncb_;
+  const long long chunk = blk / ncb_;
+#else
+  const long long chunk = blk % j.nchunks;
+  const long long cb = blk / j.nchunks;
+#endif
+  const int t = threadIdx.x;
+  const int ty = t / j.bx;
+  const int tx = t - ty * j.bx;
+  const long long cv = cb * j.bx + tx;
+  const bool active = (ty < j.by) && (cv < j.ncol);
+  const long long col0 = cv * 4;
+  // per-column constants.  Difference: kk = sigma * k1 (g_P = sign(d) * k1, sign(d) = sigma * sign(P); the product
+  // (sigma * sign(P)) * k1 of DiffBwdOp::fast1 has the same bits: sigma is +-1).  MaxBin: lo, k0 = coef / s, k1 = 0 / s.
+  bool fast = j.vec != 0;
+  float kk[4], thr[4];                                // Difference: kk;  MaxBin: kk = coef / s, thr = lo
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { kk[k] = 0.f; thr[k] = 0.f; }
+  const float gabs = kDiff ? __fmul_rn(j.t0, __ldg(up)) : 0.f;
+  if (fast && active) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long grp = (col0 + k) / j.inner;
+      const float s = __ldg(j.s + grp);
+      if (kDiff) {
+        fast = fast && diff_fast_scale(s);
+        kk[k] = __fmul_rn(s <= 0.5f ? -1.f : 1.f, __fadd_rn(gabs, __fdiv_rn(-gabs, s)));
+      } else {
+        const float4 aux = __ldg(j.gaux + grp);
+        fast = fast && aux.w >= 0.f;                  // the group's ties are the elements with |P| >= lo; s > 0 there,
+        thr[k] = aux.w;                               // so MaxBinBwdOp's other constant, 0 / s, is +0
+        kk[k] = __fdiv_rn(aux.z, s);
+      }
+    }
+  }
+  if (!__syncthreads_and(fast ? 1 : 0)) { pen_bwd_col_generic<KIND, ACCUM>(j, blk, smem, up); return; }   // block-uniform
+  const long long r0 = chunk * j.rpc;
+  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
+  const int rows_mine = active ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
+  const long long stride = (long long)j.by * j.W;
+  const long long base = active ? (r0 + ty) * j.W + col0 : 0;
+  const float* Pp = j.P + base;
+  float* Xp = j.dX + base;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};               // Difference: the exactly evaluated terms of the scale gradient
+  bool any_exact = false, redo = false;
+  const float* const Pp0 = Pp;
+  float* const Xp0 = Xp;
+#pragma unroll 1
+  for (int i0 = 0; i0 < rows_blk; i0 += U) {
+    float4 p[U], old[ACCUM ? U : 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u < rows_mine) {
+        p[u] = *reinterpret_cast<const float4*>(Pp + u * stride);
+        if (ACCUM) old[ACCUM ? u : 0] = *reinterpret_cast<const float4*>(Xp + u * stride);
+      }
+    }
+#pragma unroll
+    for (int q0 = 0; q0 < U; q0 += 4) {               // the generic traversal's quads: four rows of one column
+      const int left = rows_mine - (i0 + q0);         // this thread's rows from here on
+      if (left <= 0) continue;
+      if (kDiff) {
+        if (left < 4) continue;                       // the chunk's last 1-3 rows: after the loop
+        if (!diff_quads_ordinary(p[q0], p[q0 + 1], p[q0 + 2], p[q0 + 3])) { redo = true; continue; }   // after the loop
+#pragma unroll
+        for (int u = q0; u < q0 + 4; ++u) {
+          float4 g;
+          g.x = __fmul_rn(sgn(p[u].x), kk[0]); g.y = __fmul_rn(sgn(p[u].y), kk[1]);
+          g.z = __fmul_rn(sgn(p[u].z), kk[2]); g.w = __fmul_rn(sgn(p[u].w), kk[3]);
+          if (ACCUM) {
+            const float4 o4 = old[ACCUM ? u : 0];
+            g.x = __fadd_rn(o4.x, g.x); g.y = __fadd_rn(o4.y, g.y); g.z = __fadd_rn(o4.z, g.z); g.w = __fadd_rn(o4.w, g.w);
+          }
+          *reinterpret_cast<float4*>(Xp + u * stride) = g;
+        }
+      } else {
+#pragma unroll
+        for (int u = q0; u < q0 + 4; ++u) {
+          if (u - q0 < left) {
+            float4 g;
+            g.x = __fmul_rn((fabsf(p[u].x) >= thr[0]) ? kk[0] : 0.0f, sgn(p[u].x));
+            g.y = __fmul_rn((fabsf(p[u].y) >= thr[1]) ? kk[1] : 0.0f, sgn(p[u].y));
+            g.z = __fmul_rn((fabsf(p[u].z) >= thr[2]) ? kk[2] : 0.0f, sgn(p[u].z));
+            g.w = __fmul_rn((fabsf(p[u].w) >= thr[3]) ? kk[3] : 0.0f, sgn(p[u].w));
+            if (ACCUM) {
+              const float4 o4 = old[ACCUM ? u : 0];
+              g.x = __fadd_rn(o4.x, g.x); g.y = __fadd_rn(o4.y, g.y); g.z = __fadd_rn(o4.z, g.z); g.w = __fadd_rn(o4.w, g.w);
+            }
+            *reinterpret_cast<float4*>(Xp + u * stride) = g;
+          }
+        }
+      }
+    }
+    Pp += U * stride;
+    Xp += U * stride;
+  }
+  if (!kDiff) return;
+  // What the streaming loop left out (no call in there: it would spill the registers that hold loads in flight): the
+  // chunk's last 1-3 rows, and -- only if this thread met one -- the quads that are not ordinary, found again by
+  // re-reading the thread's rows.
+  if (rows_mine & 3) {
+    const long long off = (long long)(rows_mine & ~3) * stride;
+    const float4 a4 = diff_bwd_rows_slow<ACCUM>(j, Pp0 + off, Xp0 + off, stride, rows_mine & 3, col0, gabs);
+    acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
+    any_exact = true;
+  }
+  if (redo) {
+    for (int q = 0; q + 4 <= rows_mine; q += 4) {
+      const float* pq = Pp0 + (long long)q * stride;
+      if (diff_quads_ordinary(*reinterpret_cast<const float4*>(pq), *reinterpret_cast<const float4*>(pq + stride),
+                              *reinterpret_cast<const float4*>(pq + 2 * stride), *reinterpret_cast<const float4*>(pq + 3 * stride)))
+        continue;
+      const float4 a4 = diff_bwd_rows_slow<ACCUM>(j, pq, Xp0 + (long long)q * stride, stride, 4, col0, gabs);
+      acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
+    }
+    any_exact = true;
+  }
+  // the column partials of the scale gradient (zero unless some quad took the exact form): same tree as run_col
+  if (__syncthreads_or(any_exact ? 1 : 0) && j.by > 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { Acc a; a.a = acc[k]; a.b = 0u; a.c = 0.f; smem[k * kThreads + t] = a; }
+    int span = 1;
+    while (span < j.by) span <<= 1;
+    for (int st = span >> 1; st >= 1; st >>= 1) {
+      __syncthreads();
+      if (ty < st && ty + st < j.by) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) smem[k * kThreads + t].a += smem[k * kThreads + t + st * j.bx].a;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = smem[k * kThreads + t].a;
+  }
+  if (ty == 0 && cv < j.ncol) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) j.part[chunk * j.W + col0 + k] = make_float4(acc[k], __uint_as_float(0u), 0.f, 0.f);
+  }
+}
+
+// ROW tensors through the generic multi-tensor traversal, interleaved ones through the lean kernel above
+template <int KIND, bool ACCUM>
+static int launch_pen_bwd(JobTable& tab, const float* up, cudaStream_t st) {
+  using Op = typename BwdKind<KIND, ACCUM>::Op;
+  JobTable rows, cols;
+  rows.n = cols.n = 0;
+  unsigned total = 0;
+  for (int i = 0; i < tab.n; ++i) {
+    const Job& tj = tab.job[i];
+    if (tj.nblocks == 0) continue;
+    // (Difference on short interleaved tensors -- a model's kernels, a few rows per thread -- stays on the generic
+    // traversal: there the lean kernel's per-block constants and partial tree outweigh its loop, 35 us against 31 for
+    // the 40-tensor inventory)
+    if (tj.regime == REG_COL && tj.vec && (KIND == LQ_PEN_MAXBIN || tj.rpc / tj.by >= 16)) {
+      cols.job[cols.n] = tj;
+      cols.job[cols.n].block_begin = total;
+      total += tj.nblocks;
+      ++cols.n;
+    } else {
+      rows.job[rows.n++] = tj;
+    }
+  }
+  if (rows.n) { const int rc = launch_mt(rows, make_pen_op<Op>(up), st); if (rc) return rc; }
+  if (total) return launch_after(pen_bwd_col_kernel<KIND, ACCUM>, dim3(total), dim3(kThreads), st, "loss-term backward COL launch", cols, up);
+  return LQ_OK;
 }
 
 // Per-group stage of the backward: scale gradients that need no element pass, and the
@@ -1088,7 +1359,7 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
         gt.job[gt.n++] = gj;
       }
       if (kind != LQ_PEN_INVERSE) {
-        Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dX));
+        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dX));   // the forward's cut of the tensor
         if (g.nblocks > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
         Job j = make_job(g, d.P, d.s, d.dX, nullptr, d.dX, nullptr, 0, part);
         j.write_dx = 1;
@@ -1114,8 +1385,8 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
       if ((rc = launch_after(pen_group_kernel, dim3((groups + 127) / 128), dim3(128), st, "penalty group launch", gt, up))) break;
     }
     if (tab.n) {
-      if (kind == LQ_PEN_MAXBIN) rc = accum ? launch_mt(tab, make_pen_op<MaxBinBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<MaxBinBwdOp<false>>(up), st);
-      else rc = accum ? launch_mt(tab, make_pen_op<DiffBwdOp<true>>(up), st) : launch_mt(tab, make_pen_op<DiffBwdOp<false>>(up), st);
+      if (kind == LQ_PEN_MAXBIN) rc = accum ? launch_pen_bwd<LQ_PEN_MAXBIN, true>(tab, up, st) : launch_pen_bwd<LQ_PEN_MAXBIN, false>(tab, up, st);
+      else rc = accum ? launch_pen_bwd<LQ_PEN_DIFFERENCE, true>(tab, up, st) : launch_pen_bwd<LQ_PEN_DIFFERENCE, false>(tab, up, st);
       if (rc) break;
       if (fin.n) {
         if ((rc = pen_fold_large(fin, st))) break;
