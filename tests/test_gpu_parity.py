@@ -667,6 +667,57 @@ def test_maxbin_tie_counting_corner_cases(lq, shape, s_shape, fill):
         assert float(np.max(np.abs(got - want))) <= TOL * max(float(np.max(np.abs(want))), 1e-30)
 
 
+@pytest.mark.parametrize("shape", [(20000, 128), (30011, 132)])
+def test_penalties_interleaved_lean_kernels(lq, shape):
+    """Interleaved tensors of this size take the lean COL kernels of lq_penalty.cu (stat_col_kernel forward,
+    pen_bwd_col_kernel backward: rows per thread >= 8); the same data at an address that is not 16-byte aligned takes
+    the generic traversal.  dX must have the same bits either way, penalty and ds must agree within TOL, and both must
+    match the oracle -- with quads that are not ordinary (values beyond 2^80, re-done out of line), whole rows of zeros,
+    a chunk tail (30011 rows), a nearly empty second column block (132 columns) whose scale is outside Difference's
+    fast set (that block falls back to the generic traversal), plain and accumulate mode."""
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(shape[0])
+    K = rng.normal(0, 0.05, size=shape).astype(np.float32)
+    K[17, :] = 0.0; K[18, 5] = -0.0
+    sK = rng.uniform(5e-3, 2e-2, size=(1, shape[1])).astype(np.float32)
+    if shape[1] > 128:                                                  # (the first shape stays ordinary: a strict ds check)
+        K[5, 3] = 1e25; K[100, 7] = -3e24; K[shape[0] - 2, 9] = 2e24   # > 2^80 = 1.2e24: their quads are not ordinary
+        sK[0, 130] = 1.0                                                # not in Difference's fast set (1/2 < s < 2)
+    b = rng.normal(0, 0.05, size=(shape[1],)).astype(np.float32)
+    sb = np.array([0.01], np.float32)
+    layers = [(K, sK, b, sb)]
+    n = K.size
+    buf = torch.empty(n + 1, device="cuda")
+    buf[1:].copy_(dev(K).reshape(-1))
+    K_unaligned = buf[1:].view(shape)
+    assert K_unaligned.data_ptr() % 16 != 0
+    for kind, val, grad in ((_lib.LQ_PEN_MAXBIN, o.maxbin_penalty, o.maxbin_penalty_grads),
+                            (_lib.LQ_PEN_DIFFERENCE, o.difference_penalty, o.difference_penalty_grads)):
+        ref_val = val(layers)
+        (gK, gsK, gb, gsb), = grad(layers, 1.0, accum="fp64")
+        results = []
+        for Kt in (dev(K), K_unaligned):
+            Ps, ss = [Kt, dev(b)], [dev(sK), dev(sb)]
+            out, ws = ops.penalty_fwd(kind, Ps, ss)
+            assert rel_err(host(out), ref_val) < TOL, kind
+            dX0 = torch.empty(n + 1, device="cuda")[1:].view(shape) if Kt is K_unaligned else torch.empty_like(Kt)
+            dXs, dss = ops.penalty_bwd(kind, Ps, ss, ws, 1.0, dXs=[dX0, torch.empty_like(Ps[1])],
+                                       dss=[torch.empty_like(ss[0]), torch.empty_like(ss[1])])
+            scale = max(float(np.max(np.abs(gK))), 1e-30)
+            assert float(np.max(np.abs(host(dXs[0]).astype(np.float64) - gK))) <= TOL * scale, kind
+            assert ds_err(host(dss[0]), gsK) <= TOL, kind
+            acc_dX = [torch.ones(n + 1, device="cuda")[1:].view(shape) if Kt is K_unaligned else torch.ones_like(Kt),
+                      torch.ones_like(Ps[1])]
+            acc_ds = [torch.ones_like(s) for s in ss]
+            ops.penalty_bwd(kind, Ps, ss, ws, 2.5, dXs=acc_dX, dss=acc_ds, accumulate=True)
+            assert float(np.max(np.abs(host(acc_dX[0]).astype(np.float64) - 1.0 - 2.5 * gK))) <= 1e-6 + 3 * TOL * scale, kind
+            results.append((host(out), host(dXs[0]).copy(), host(dss[0]).copy(), host(acc_dX[0]).copy()))
+        (o1, d1, s1, a1), (o2, d2, s2, a2) = results
+        assert bits_equal(d1, d2) and bits_equal(a1, a2), kind            # lean == generic, bit for bit
+        assert rel_err(o1, o2) < TOL and ds_err(s1, s2) <= TOL, kind
+
+
 def test_penalties_many_tensors_and_a_huge_group(lq):
     """More tensors than one kernel-parameter table holds (the scalar stage chains over launches) and a
     per-tensor scale on a 9.4 M-element kernel (more than 4096 partials: the two-level fold)."""
