@@ -1183,13 +1183,19 @@ static int pen_fold_large(FinTable& fin, cudaStream_t st) {
 // per row), eight threads deep, LONG row chunks -- the second stage walks chunks-per-group partials, and with the
 // element kernels' 64-row chunks a [131072, 512] tensor had 2048 of them per group (25 us of second stage for a
 // 45 us pass).  Never more partials than the default geometry the workspace is sized for.
+#ifndef LQ_STAT_BX
+#define LQ_STAT_BX 32
+#endif
+#ifndef LQ_STAT_BPS
+#define LQ_STAT_BPS 8
+#endif
 static Geom make_stat_geom(long long outer, long long C, long long inner, bool aligned) {
   Geom g = make_geom(outer, C, inner, aligned);
   if (g.regime != REG_COL || !g.vec_ok) return g;
-  const int bx = g.ncol < 32 ? (int)g.ncol : 32;
+  const int bx = g.ncol < LQ_STAT_BX ? (int)g.ncol : LQ_STAT_BX;
   const int by = kThreads / bx;
   const long long ncolblk = cdiv(g.ncol, bx);
-  long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * 8), by) * by;
+  long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * LQ_STAT_BPS), by) * by;
   if (rpc < by) rpc = by;
   if (rpc > 1024) rpc = 1024 / by * by;
   if (rpc > outer) rpc = outer;
