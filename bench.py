@@ -512,6 +512,11 @@ def run_ours(args):
                     raise
         if world == 1:
             extra["mnist_cpu"] = mnist_cpu()
+            for key, fn in (("layouts_64Mi", lambda: other_layouts_64mi(args.steps)), ("loss_terms_64Mi", loss_terms_64mi)):
+                try:
+                    extra[key] = fn()
+                except Exception as e:            # reported, never allowed to take the headline line down
+                    extra[key] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         line.update(extra)
         print(json.dumps(line))
@@ -870,16 +875,86 @@ def sweep_variants():
     return out
 
 
-def run_sweep(args):
-    """Not the headline: one JSON line per (layout, size) with fwd/bwd device times (median of
-    --steps launches each, CUDA events), written to stdout; arrays rotate so that the working
-    set of consecutive launches exceeds L2."""
+def time_layout(name, layout, scales, lam, steps, warmup, gen, peak):
+    """fwd / bwd device times of one layout (median over five batches of `steps` launches between two events, or a CUDA
+    graph of `steps` launches for the launch-bound sizes); arrays rotate so that consecutive launches exceed L2."""
     import torch
     import learned_quantization_b200 as lq
     ops, lib, check = lq.ops, lq._lib.lib, lq._lib.check
-    torch.cuda.set_device(0)
-    stream = torch.cuda.current_stream().cuda_stream
     ninf, pinf = float("-inf"), float("inf")
+    n = layout[0] * layout[1] * layout[2]
+    nsets = max(2, min(16, -(-(600 << 20) // (12 * n))))
+    if scales == "trained":
+        s = torch.empty(layout[1], device="cuda").uniform_(5e-3, 2e-2, generator=gen)
+    else:
+        s = torch.full((layout[1],), 1.1920928955078125e-05, device="cuda")        # NQ:156-158
+    Ps = [torch.empty(n, device="cuda").normal_(0, 0.05, generator=gen) for _ in range(nsets)]
+    dys = [torch.empty(n, device="cuda").normal_(0, 1e-3, generator=gen) for _ in range(nsets)]
+    outs = [torch.empty(n, device="cuda") for _ in range(nsets)]
+    ds = torch.empty(layout[1], device="cuda")
+    ws = torch.empty(max(ops.workspace_bytes([ops.make_desc(layout=layout)], lq._lib.LQ_PHASE_BWD), 256),
+                     dtype=torch.uint8, device="cuda")
+
+    def fwd(i):
+        check(lib.lq_fq_fwd(Ps[i].data_ptr(), s.data_ptr(), outs[i].data_ptr(), None, 0, *layout, 0, ninf, pinf,
+                            torch.cuda.current_stream().cuda_stream))
+
+    def bwd(i):
+        check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), lam, outs[i].data_ptr(),
+                                      ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream().cuda_stream))
+
+    res = {}
+    graphed = n <= (1 << 24)      # launch-bound sizes: time a CUDA graph of `steps` launches
+    for tag, fn in (("fwd", fwd), ("bwd", bwd)):
+        for i in range(max(warmup, 3)):
+            fn(i % nsets)
+        torch.cuda.synchronize()
+        if graphed:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(steps):
+                    fn(i % nsets)
+            g.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); g.replay(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) / steps)
+            res[tag] = sorted(ts)[len(ts) // 2]
+            del g
+        else:
+            # like the headline: `steps` launches between two events (an event record costs ~3 us of stream
+            # time, which a per-launch bracket would charge to every launch); median of five such batches
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            k = 0
+            for a, b in evs:
+                a.record()
+                for _ in range(steps):
+                    fn(k % nsets); k += 1
+                b.record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) / steps for a, b in evs)
+            res[tag] = ts[len(ts) // 2]
+    gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
+    out = {"layout_name": name, "layout": list(layout), "elements": n, "scales": scales, "lambda": lam,
+           "rotating_sets": nsets,
+           "timing": f"CUDA graph of {steps} launches" if graphed else f"{steps} launches between two CUDA events, median of 5",
+           "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
+           "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),
+           "fwd_bwd_GBps": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9,
+           "frac_of_measured_peak": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9 / peak}
+    del Ps, dys, outs
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sweep(args):
+    """Not the headline: one JSON line per (layout, size) with fwd/bwd device times, written to stdout."""
+    import torch
+    torch.cuda.set_device(0)
     peak, _ = measured_peak()
     gen = torch.Generator(device="cuda").manual_seed(42)
     only = set(args.only.split(",")) if args.only else None
@@ -887,72 +962,70 @@ def run_sweep(args):
         n = layout[0] * layout[1] * layout[2]
         if n > args.max_elems or (only and name not in only):
             continue
-        nsets = max(2, min(16, -(-(600 << 20) // (12 * n))))
-        if scales == "trained":
-            s = torch.empty(layout[1], device="cuda").uniform_(5e-3, 2e-2, generator=gen)
-        else:
-            s = torch.full((layout[1],), 1.1920928955078125e-05, device="cuda")        # NQ:156-158
-        Ps = [torch.empty(n, device="cuda").normal_(0, 0.05, generator=gen) for _ in range(nsets)]
-        dys = [torch.empty(n, device="cuda").normal_(0, 1e-3, generator=gen) for _ in range(nsets)]
-        outs = [torch.empty(n, device="cuda") for _ in range(nsets)]
-        ds = torch.empty(layout[1], device="cuda")
-        ws = torch.empty(max(ops.workspace_bytes([ops.make_desc(layout=layout)], lq._lib.LQ_PHASE_BWD), 256),
-                         dtype=torch.uint8, device="cuda")
+        print(json.dumps(time_layout(name, layout, scales, lam, args.steps, args.warmup, gen, peak)), flush=True)
 
-        def fwd(i):
-            check(lib.lq_fq_fwd(Ps[i].data_ptr(), s.data_ptr(), outs[i].data_ptr(), None, 0, *layout, 0, ninf, pinf,
-                                torch.cuda.current_stream().cuda_stream))
 
-        def bwd(i):
-            check(lib.lq_fq_bwd_threshold(dys[i].data_ptr(), Ps[i].data_ptr(), s.data_ptr(), lam, outs[i].data_ptr(),
-                                          ds.data_ptr(), *layout, 0, ninf, pinf, ws.data_ptr(), ws.numel(),
-                                          torch.cuda.current_stream().cuda_stream))
+def other_layouts_64mi(steps):
+    """Extra key of the default line (N = 1): the other two traversal regimes at the headline size -- per-tensor scale
+    (ROW, one group) and the interleaved layout (COL: register forward, TMA-staged backward) -- beside the headline's
+    channelwise [256, 512, 512].  Same timing method as the headline."""
+    import torch
+    peak, _ = measured_peak()
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    n = 1 << 26
+    out = {}
+    for name, layout in (("per_tensor", (1, 1, n)), ("interleaved_C512", (n // 512, 512, 1))):
+        r = time_layout(name, layout, "trained", LAMBDA, steps, 3, gen, peak)
+        out[name] = {k: r[k] for k in ("layout", "fwd_us", "bwd_us", "fwd_bwd_GBps", "frac_of_measured_peak", "timing")}
+    return out
 
-        res = {}
-        graphed = n <= (1 << 24)      # launch-bound sizes: time a CUDA graph of `steps` launches
-        for tag, fn in (("fwd", fwd), ("bwd", bwd)):
-            for i in range(max(args.warmup, 3)):
-                fn(i % nsets)
+
+def loss_terms_64mi():
+    """Extra key of the default line (N = 1): the custom-loss reductions (LF:75-116 / 161-195) on the three 64 Mi
+    layouts, forward (4 B/elem: read P) and backward (8 B/elem: read P, write dX); GPU time per call from a CUDA graph
+    of ten calls, fraction of the measured copy peak."""
+    import torch
+    import learned_quantization_b200 as lq
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    peak, _ = measured_peak()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record()
             torch.cuda.synchronize()
-            if graphed:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for i in range(args.steps):
-                        fn(i % nsets)
-                g.replay()
-                torch.cuda.synchronize()
-                ts = []
-                for _ in range(5):
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(); g.replay(); b.record()
-                    torch.cuda.synchronize()
-                    ts.append(a.elapsed_time(b) / args.steps)
-                res[tag] = sorted(ts)[len(ts) // 2]
-                del g
-            else:
-                # like the headline: `steps` launches between two events (an event record costs ~3 us of stream
-                # time, which a per-launch bracket would charge to every launch); median of five such batches
-                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-                k = 0
-                for a, b in evs:
-                    a.record()
-                    for _ in range(args.steps):
-                        fn(k % nsets); k += 1
-                    b.record()
-                torch.cuda.synchronize()
-                ts = sorted(a.elapsed_time(b) / args.steps for a, b in evs)
-                res[tag] = ts[len(ts) // 2]
-        gb = lambda bpe, ms: bpe * n / (ms * 1e-3) / 1e9
-        print(json.dumps({"layout_name": name, "layout": list(layout), "elements": n, "scales": scales, "lambda": lam,
-                          "rotating_sets": nsets,
-                          "timing": f"CUDA graph of {args.steps} launches" if graphed else f"{args.steps} launches between two CUDA events, median of 5",
-                          "fwd_us": res["fwd"] * 1e3, "bwd_us": res["bwd"] * 1e3,
-                          "fwd_GBps": gb(BYTES_FWD, res["fwd"]), "bwd_GBps": gb(BYTES_BWD, res["bwd"]),
-                          "fwd_bwd_GBps": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9,
-                          "frac_of_measured_peak": (BYTES_FWD + BYTES_BWD) * n / ((res["fwd"] + res["bwd"]) * 1e-3) / 1e9 / peak}),
-              flush=True)
-        del Ps, dys, outs
+            ts.append(a.elapsed_time(b) / reps * 1e3)
+        return sorted(ts)[1]
+
+    out = {}
+    n = 1 << 26
+    for name, shape, sshape in (("channelwise_256x512x512", (256, 512, 512), (1, 512, 1)), ("per_tensor", (n,), (1,)),
+                                ("interleaved_131072x512", (131072, 512), (1, 512))):
+        P = [torch.empty(shape, device="cuda").normal_(0, 0.05, generator=gen)]
+        s = [torch.empty(sshape, device="cuda").uniform_(5e-3, 2e-2, generator=gen)]
+        dX, dS = [torch.empty_like(P[0])], [torch.empty_like(s[0])]
+        for kname, kind in (("maxbin", _lib.LQ_PEN_MAXBIN), ("difference", _lib.LQ_PEN_DIFFERENCE)):
+            _, ws = ops.penalty_fwd(kind, P, s)
+            f_us = timed(lambda: ops.penalty_fwd(kind, P, s))
+            b_us = timed(lambda: ops.penalty_bwd(kind, P, s, ws, 1.0, dXs=dX, dss=dS))
+            out[f"{name}/{kname}"] = {"fwd_us": f_us, "bwd_us": b_us,
+                                      "fwd_frac_of_measured_peak": 4 * n / (f_us * 1e-6) / 1e9 / peak,
+                                      "bwd_frac_of_measured_peak": 8 * n / (b_us * 1e-6) / 1e9 / peak}
+        del P, dX
         torch.cuda.empty_cache()
+    return out
 
 
 def protect_stdout():

@@ -52,3 +52,7 @@ def test_gpu_arm_line():
     assert d["roofline"]["traffic"] is None or "unchanged" in d["roofline"]["traffic_source"]
     assert 0 < d["e2e"]["frac_of_pcie_bound"] <= 1.2
     assert d["value"] > 3000, "fwd+bwd below half of the HBM roofline: something is wrong with the build"
+    lay = d["layouts_64Mi"]                      # the other two traversal regimes at the headline size
+    assert "error" not in lay and lay["interleaved_C512"]["frac_of_measured_peak"] > 0.8 and lay["per_tensor"]["frac_of_measured_peak"] > 0.8
+    lt = d["loss_terms_64Mi"]                    # custom-loss reductions on the three layouts
+    assert "error" not in lt and len(lt) == 6 and all(v["fwd_us"] > 0 and v["bwd_us"] > 0 for v in lt.values())
