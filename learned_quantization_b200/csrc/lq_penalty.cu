@@ -242,9 +242,7 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
     sg = (int)(unit - row * j.nseg);
     grp = row % j.C;
   }
-  const float s = __ldg(j.s + grp);
-  const bool fast = (KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s);
-  if (!fast || !j.vec || j.seg > 1024) { stat_row_generic<KIND>(j, unit); return; }      // warp-uniform
+  if (!j.vec || j.seg > 1024) { stat_row_generic<KIND>(j, unit); return; }                // per tensor
   const long long base = row * j.inner + (long long)sg * j.seg;
   const long long rem = j.inner - (long long)sg * j.seg;
   const int nvec = (rem < j.seg ? (int)rem : j.seg) >> 2;                                 // <= 256: one trip
@@ -255,6 +253,10 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
     const int v = u * 32 + lane;
     if (v < nvec) p[u] = j.stream_hint ? __ldcs(P4 + v) : P4[v];
   }
+  // the scale is looked at AFTER the unit's loads have been issued: with the regime test in front of them every warp
+  // spent one round trip to memory on four bytes before it asked for its 4 KB
+  const float s = __ldg(j.s + grp);
+  const bool fast = (KIND == LQ_PEN_MAXBIN) ? maxbin_fast_scale(s) : diff_fast_scale(s);
   float m = -1.f, a = 0.f;
   bool bad = false;
 #pragma unroll
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 4) stat_row_kernel(const __grid_cons
       }
     }
   }
-  if (KIND == LQ_PEN_DIFFERENCE && __any_sync(0xffffffffu, bad)) { stat_row_generic<KIND>(j, unit); return; }
+  if (!fast || (KIND == LQ_PEN_DIFFERENCE && __any_sync(0xffffffffu, bad))) { stat_row_generic<KIND>(j, unit); return; }   // warp-uniform
   if (KIND == LQ_PEN_MAXBIN) {
     // m is -1 or >= 0 and never NaN: as signed integers the bit patterns order like the values
     m = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(m)));
@@ -334,6 +336,21 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
   const long long cv = cb * j.bx + tx;
   const bool active = (ty < j.by) && (cv < j.ncol);
   const long long col0 = cv * 4;
+  const long long r0 = chunk * j.rpc;
+  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
+  const int rows_mine = (active && j.vec) ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
+  const long long stride = (long long)j.by * j.W;
+  const float* Pp = j.P + (active ? (r0 + ty) * j.W + col0 : 0);
+  auto ldrow = [&](const float* q) {
+    return j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(q)) : *reinterpret_cast<const float4*>(q);
+  };
+  // the first eight rows are asked for BEFORE the scales are looked at (the regime test in front of the loop cost every
+  // block one round trip to memory on sixteen bytes); a block that turns out not to be in the fast regime drops them
+  float4 p[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (u < rows_mine) p[u] = ldrow(Pp + u * stride);
   bool fast = j.vec != 0;
   if (fast && active) {
 #pragma unroll
@@ -343,23 +360,12 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
     }
   }
   if (!__syncthreads_and(fast ? 1 : 0)) { stat_col_generic<KIND>(j, blk, smem); return; }   // block-uniform
-  const long long r0 = chunk * j.rpc;
-  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
-  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
-  const int rows_mine = active ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
-  const long long stride = (long long)j.by * j.W;
-  const float* Pp = j.P + (active ? (r0 + ty) * j.W + col0 : 0);
   float v[4];                                       // MaxBin: max |P| ; Difference: sum |P|, per column
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k] = (KIND == LQ_PEN_MAXBIN) ? -1.f : 0.f;
   bool bad = false;
 #pragma unroll 1
   for (int i0 = 0; i0 < rows_blk; i0 += 8) {
-    float4 p[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (i0 + u < rows_mine) p[u] = j.stream_hint ? __ldcs(reinterpret_cast<const float4*>(Pp + u * stride))
-                                                   : *reinterpret_cast<const float4*>(Pp + u * stride);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (i0 + u < rows_mine) {
@@ -372,6 +378,9 @@ __global__ void __launch_bounds__(kThreads, 4) stat_col_kernel(const __grid_cons
       }
     }
     Pp += 8 * stride;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)                        // the next eight rows
+      if (i0 + 8 + u < rows_mine) p[u] = ldrow(Pp + u * stride);
   }
   if (KIND == LQ_PEN_DIFFERENCE) {
     bad = !(((v[0] + v[1]) + (v[2] + v[3])) <= kFastHi);       // an inf or a NaN anywhere in the thread's columns
@@ -970,6 +979,23 @@ __global__ void __launch_bounds__(kThreads, LQ_PENB_MINBLK) pen_bwd_col_kernel(c
   const long long cv = cb * j.bx + tx;
   const bool active = (ty < j.by) && (cv < j.ncol);
   const long long col0 = cv * 4;
+  const long long r0 = chunk * j.rpc;
+  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
+  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
+  const int rows_mine = (active && j.vec) ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
+  const long long stride = (long long)j.by * j.W;
+  const long long base = active ? (r0 + ty) * j.W + col0 : 0;
+  const float* Pp = j.P + base;
+  float* Xp = j.dX + base;
+  // the first trip's rows are asked for BEFORE the per-column constants (several IEEE divisions) and the regime vote
+  float4 p[U], old[ACCUM ? U : 1];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < rows_mine) {
+      p[u] = *reinterpret_cast<const float4*>(Pp + u * stride);
+      if (ACCUM) old[ACCUM ? u : 0] = *reinterpret_cast<const float4*>(Xp + u * stride);
+    }
+  }
   // per-column constants.  Difference: kk = sigma * k1 (g_P = sign(d) * k1, sign(d) = sigma * sign(P); the product
   // (sigma * sign(P)) * k1 of DiffBwdOp::fast1 has the same bits: sigma is +-1).  MaxBin: lo, k0 = coef / s, k1 = 0 / s.
   bool fast = j.vec != 0;
@@ -994,28 +1020,12 @@ __global__ void __launch_bounds__(kThreads, LQ_PENB_MINBLK) pen_bwd_col_kernel(c
     }
   }
   if (!__syncthreads_and(fast ? 1 : 0)) { pen_bwd_col_generic<KIND, ACCUM>(j, blk, smem, up); return; }   // block-uniform
-  const long long r0 = chunk * j.rpc;
-  const long long r1 = (r0 + j.rpc < j.outer) ? r0 + j.rpc : j.outer;
-  const int rows_blk = (int)((r1 - r0 + j.by - 1) / j.by);
-  const int rows_mine = active ? (int)((r1 - r0 - ty + j.by - 1) / j.by) : 0;
-  const long long stride = (long long)j.by * j.W;
-  const long long base = active ? (r0 + ty) * j.W + col0 : 0;
-  const float* Pp = j.P + base;
-  float* Xp = j.dX + base;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};               // Difference: the exactly evaluated terms of the scale gradient
   bool any_exact = false, redo = false;
   const float* const Pp0 = Pp;
   float* const Xp0 = Xp;
 #pragma unroll 1
   for (int i0 = 0; i0 < rows_blk; i0 += U) {
-    float4 p[U], old[ACCUM ? U : 1];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i0 + u < rows_mine) {
-        p[u] = *reinterpret_cast<const float4*>(Pp + u * stride);
-        if (ACCUM) old[ACCUM ? u : 0] = *reinterpret_cast<const float4*>(Xp + u * stride);
-      }
-    }
 #pragma unroll
     for (int q0 = 0; q0 < U; q0 += 4) {               // the generic traversal's quads: four rows of one column
       const int left = rows_mine - (i0 + q0);         // this thread's rows from here on
@@ -1054,6 +1064,13 @@ __global__ void __launch_bounds__(kThreads, LQ_PENB_MINBLK) pen_bwd_col_kernel(c
     }
     Pp += U * stride;
     Xp += U * stride;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                     // the next trip's rows
+      if (i0 + U + u < rows_mine) {
+        p[u] = *reinterpret_cast<const float4*>(Pp + u * stride);
+        if (ACCUM) old[ACCUM ? u : 0] = *reinterpret_cast<const float4*>(Xp + u * stride);
+      }
+    }
   }
   if (!kDiff) return;
   // What the streaming loop left out (no call in there: it would spill the registers that hold loads in flight): the
