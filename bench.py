@@ -824,7 +824,10 @@ def run_qat(args, rank, world, local, key="qat"):
                       "launch": "eager" if args.qat_eager else
                       ("one CUDA graph per step" if (world == 1 or peer) else "three CUDA graphs per step around the NCCL call")},
            "allreduce_floats": step.bucket.n_exact,
-           "our_launches_per_step": {"lq_mt_fq_fwd": 1,
+           "our_launches_per_step": {("lq_mt_fq_fwd_penalty (forward + loss term in one pass)" if getattr(step, "fused_loss", False)
+                                      else "lq_mt_fq_fwd"): 1,
+                                     "lq_penalty_fwd": 1 if (variant == "custom_loss" and not getattr(step, "fused_loss", False)) else 0,
+                                     "lq_penalty_bwd": 1 if variant == "custom_loss" else 0,
                                      "lq_mt_fq_bwd": (2 if threshold else 0) if not peer else 0,
                                      "lq_dpx_exchange": (2 if threshold else 1) if peer else 0,
                                      ("lq_opt_sgd" if cifar else "lq_opt_adam"): -(-len(step.table.params) // 56),

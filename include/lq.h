@@ -141,6 +141,15 @@ int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, float* out_pena
 int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, float upstream,
                    const float* upstream_dev, void* ws, size_t ws_bytes, lq_stream_t stream);
 
+/* The forward of every tensor AND the MaxBin / Difference loss term over them in ONE pass (the penalty
+ * forward "fused into K1: 0 extra bytes"; reference: the forward at NQ:55-60 and compute_*_penalty at LF:75-116 /
+ * 161-195 read the same kernels and biases in the same step).  desc.y = floor(P / s) * s is written exactly as
+ * lq_mt_fq_fwd writes it; out_penalty and the workspace are left exactly as lq_penalty_fwd(kind, ...) leaves them, so
+ * the matching lq_penalty_bwd call works unchanged.  ws: lq_workspace_bytes(descs, n, LQ_PHASE_PENALTY_FWD).
+ * LQ_PEN_INVERSE (which reads no tensor) is refused with LQ_E_BADMODE. */
+int lq_mt_fq_fwd_penalty(int kind, const lq_tensor_desc* descs, int n, int round_mode, float qmin, float qmax,
+                         float* out_penalty, void* ws, size_t ws_bytes, lq_stream_t stream);
+
 /* K5 multi-tensor forms: ONE launch per phase over all descs (the models quantise 4-42
  * small tensors per step; per-tensor launches dominate there). */
 int lq_mt_fq_fwd(const lq_tensor_desc* descs, int n, int round_mode, float qmin, float qmax,

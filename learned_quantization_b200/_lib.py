@@ -63,6 +63,7 @@ SIGNATURES = {
     "lq_scale_constraint": (_I, [_P, _I64, _F, _P]),
     "lq_penalty_fwd": (_I, [_I, _DESCS, _I, _P, _P, _SZ, _P]),
     "lq_penalty_bwd": (_I, [_I, _DESCS, _I, _F, _P, _P, _SZ, _P]),
+    "lq_mt_fq_fwd_penalty": (_I, [_I, _DESCS, _I, _I, _F, _F, _P, _P, _SZ, _P]),
     "lq_mt_fq_fwd": (_I, [_DESCS, _I, _I, _F, _F, _P]),
     "lq_mt_fq_bwd": (_I, [_DESCS, _I, _F, _I, _I, _F, _F, _P, _SZ, _P]),
     "lq_host_workspace_bytes": (_I, [_I64, _I64, _I64, C.POINTER(_SZ)]),

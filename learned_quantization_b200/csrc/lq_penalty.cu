@@ -208,6 +208,40 @@ __device__ __forceinline__ void zero_ctl(unsigned* ctl) {
   if (ctl && blockIdx.x == 0 && threadIdx.x < kCtlWords) ctl[threadIdx.x] = 0u;
 }
 
+// K1 with the loss term's statistics as by-products of the same pass ("penalty forward fused into K1:
+// 0 extra bytes"): y = floor(P / s) * s is written exactly as FwdOp (lq_fq.cu) writes it, and the unit's partial is the
+// statistics operator's, so the second stage, the tie counting and the backward are the stand-alone pass's.
+template <int KIND, bool EXT>
+struct FwdPenOp : OpBase<FwdPenOp<KIND, EXT>> {
+  using Stat = typename StatKind<KIND>::Op;
+  using Ctx = PenCtx;
+  QMode qm;
+  static constexpr bool kIn2 = false, kOutIsY = true, kCodes = false, kReduce = true, kAux = false;
+  __device__ static void init(Acc& a) { Stat::init(a); }
+  __device__ static void combine(Acc& x, const Acc& y) { Stat::combine(x, y); }
+  __device__ __forceinline__ PenCtx prep(float s, const float4& aux, const Job& j) const { return Stat().prep(s, aux, j); }
+  __device__ __forceinline__ Acc warp_reduce(const Acc& x) const { return Stat().warp_reduce(x); }
+  __device__ __forceinline__ void elem(float p, float, const PenCtx& c, const Job& j, Acc& acc, float& y, float& q) const {
+    q = round_code<EXT>(div_by(p, c.rc), qm);                    // NQ:56-57
+    y = __fmul_rn(q, c.rc.s);                                    // NQ:58
+    float o0, o1;
+    Stat().elem(p, 0.f, c, j, acc, o0, o1);
+  }
+  __device__ __forceinline__ void quad(const float4& p, const float4& d, const PenCtx& c, const Job& j, Acc& acc,
+                                       float4& y, float4& q, Defer& df) const {
+    if (c.rc.fast && fast_range4(p)) {        // one guard for the four elements, as in FwdOp::quad
+      q.x = round_code<EXT>(div_fast(p.x, c.rc), qm); q.y = round_code<EXT>(div_fast(p.y, c.rc), qm);
+      q.z = round_code<EXT>(div_fast(p.z, c.rc), qm); q.w = round_code<EXT>(div_fast(p.w, c.rc), qm);
+    } else {
+      q.x = round_code<EXT>(__fdiv_rn(p.x, c.rc.s), qm); q.y = round_code<EXT>(__fdiv_rn(p.y, c.rc.s), qm);
+      q.z = round_code<EXT>(__fdiv_rn(p.z, c.rc.s), qm); q.w = round_code<EXT>(__fdiv_rn(p.w, c.rc.s), qm);
+    }
+    y.x = __fmul_rn(q.x, c.rc.s); y.y = __fmul_rn(q.y, c.rc.s); y.z = __fmul_rn(q.z, c.rc.s); y.w = __fmul_rn(q.w, c.rc.s);
+    float4 o0, o1;
+    Stat().quad(p, d, c, j, acc, o0, o1, df);
+  }
+};
+
 template <int KIND>
 __device__ __noinline__ void stat_row_generic(const Job& j, long long unit) {
   typename StatKind<KIND>::Op op;
@@ -1278,13 +1312,20 @@ static int pen_check(const char* who, int kind, const lq_tensor_desc* descs, int
 
 using namespace lq;
 
-extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, float* out_penalty,
-                              void* ws, size_t ws_bytes, lq_stream_t stream) {
+// fwd != nullptr: the element pass is the fake-quant forward itself (FwdPenOp: writes desc.y, statistics as by-products)
+static int pen_fwd_impl(const char* who, int kind, const lq_tensor_desc* descs, int n, float* out_penalty,
+                        void* ws, size_t ws_bytes, cudaStream_t st, const QMode* fwd) {
   PenLayout* lay = nullptr; size_t soff = 0; double nrm = 0.0;
-  int rc = pen_check("lq_penalty_fwd", kind, descs, n, ws, ws_bytes, &lay, &soff, &nrm);
+  int rc = pen_check(who, kind, descs, n, ws, ws_bytes, &lay, &soff, &nrm);
   if (rc) return rc;
-  if (!out_penalty) { delete[] lay; set_error("lq_penalty_fwd: null out_penalty"); return LQ_E_NULLPTR; }
-  cudaStream_t st = (cudaStream_t)stream;
+  if (!out_penalty) { delete[] lay; set_error("%s: null out_penalty", who); return LQ_E_NULLPTR; }
+  if (fwd) {
+    if (kind == LQ_PEN_INVERSE) { delete[] lay; set_error("%s: the Inverse term reads no tensor: use lq_mt_fq_fwd + lq_penalty_fwd", who); return LQ_E_BADMODE; }
+    for (int i = 0; i < n; ++i)
+      if (descs[i].outer * descs[i].C * descs[i].inner != 0 && !descs[i].y) {
+        delete[] lay; set_error("%s: desc %d has null y", who, i); return LQ_E_NULLPTR;
+      }
+  }
   char* base = static_cast<char*>(ws);
   double* total = reinterpret_cast<double*>(base + soff);
   for (int i0 = 0; i0 < n && !rc; i0 += kMaxMT) {
@@ -1299,9 +1340,9 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
       float4* part = reinterpret_cast<float4*>(base + lay[i].part_off);
       float4* gstat = reinterpret_cast<float4*>(base + lay[i].gstat_off);
       if (kind != LQ_PEN_INVERSE) {
-        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P));
+        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && (!fwd || aligned16(d.y)));
         if (g.nblocks > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
-        Job j = make_job(g, d.P, d.s, nullptr, nullptr, nullptr, nullptr, 0, part);
+        Job j = make_job(g, d.P, d.s, nullptr, fwd ? d.y : nullptr, nullptr, nullptr, 0, part);
         j.gaux = gstat;                                           // pen_ties_kernel: the group's {max, ties, -, lo}
         tab.job[tab.n++] = j;
         long long nb = cdiv(g.npart1, 256);
@@ -1324,7 +1365,17 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
     unsigned* ctl = LQ_PEN_FUSED ? reinterpret_cast<unsigned*>(base + soff + kPenCtlOff) : nullptr;
     double* term = reinterpret_cast<double*>(base + soff + kPenTermOff);
     if (tab.n) {
-      if (kind == LQ_PEN_MAXBIN) rc = launch_stat<LQ_PEN_MAXBIN>(tab, st, ctl);
+      if (fwd) {
+        // the generic multi-tensor traversal knows nothing of the epilogue's counters: zeroed by a memset node here
+        if (ctl && (rc = cuda_fail(cudaMemsetAsync(ctl, 0, sizeof(unsigned) * kCtlWords, st), "zero epilogue counters"))) break;
+        if (kind == LQ_PEN_MAXBIN) {
+          if (fwd->ext) { FwdPenOp<LQ_PEN_MAXBIN, true> op; op.qm = *fwd; rc = launch_mt(tab, op, st); }
+          else { FwdPenOp<LQ_PEN_MAXBIN, false> op; op.qm = *fwd; rc = launch_mt(tab, op, st); }
+        } else {
+          if (fwd->ext) { FwdPenOp<LQ_PEN_DIFFERENCE, true> op; op.qm = *fwd; rc = launch_mt(tab, op, st); }
+          else { FwdPenOp<LQ_PEN_DIFFERENCE, false> op; op.qm = *fwd; rc = launch_mt(tab, op, st); }
+        }
+      } else if (kind == LQ_PEN_MAXBIN) rc = launch_stat<LQ_PEN_MAXBIN>(tab, st, ctl);
       else rc = launch_stat<LQ_PEN_DIFFERENCE>(tab, st, ctl);
       if (rc) break;
       if ((rc = pen_fold_large(fin, st))) break;
@@ -1340,6 +1391,19 @@ extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, floa
   }
   delete[] lay;
   return rc;
+}
+
+extern "C" int lq_penalty_fwd(int kind, const lq_tensor_desc* descs, int n, float* out_penalty,
+                              void* ws, size_t ws_bytes, lq_stream_t stream) {
+  return pen_fwd_impl("lq_penalty_fwd", kind, descs, n, out_penalty, ws, ws_bytes, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int lq_mt_fq_fwd_penalty(int kind, const lq_tensor_desc* descs, int n, int round_mode, float qmin, float qmax,
+                                    float* out_penalty, void* ws, size_t ws_bytes, lq_stream_t stream) {
+  int rc = 0;
+  QMode qm = make_qmode(round_mode, qmin, qmax, &rc);
+  if (rc) return rc;
+  return pen_fwd_impl("lq_mt_fq_fwd_penalty", kind, descs, n, out_penalty, ws, ws_bytes, (cudaStream_t)stream, &qm);
 }
 
 extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, float upstream,

@@ -41,6 +41,27 @@ class _Penalty(torch.autograd.Function):
         return tuple(grads)
 
 
+class _PenaltyFromForward(torch.autograd.Function):
+    """The same term when the step's multi-tensor forward has already produced its value and workspace as by-products
+    (lq_mt_fq_fwd_penalty through training.step.QuantBank): no second pass over the tensors; the backward is _Penalty's."""
+
+    @staticmethod
+    def forward(ctx, kind, fused, *tensors):
+        ctx.kind, ctx.fused = kind, fused
+        ctx.s_shapes = [t.shape for t in tensors[1::2]]
+        return fused["out"].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        f = ctx.fused
+        dXs, dss = ops.penalty_bwd(ctx.kind, f["Ps"], f["ss"], f["ws"], 1.0,
+                                   upstream_dev=g.detach().contiguous().to(torch.float32), layouts=f["layouts"])
+        grads = [None, None]
+        for dx, ds, shp in zip(dXs, dss, ctx.s_shapes):
+            grads += [dx, ds.view(shp)]
+        return tuple(grads)
+
+
 def _layer_tensors(layers):
     tensors = []
     for layer in layers:
@@ -75,7 +96,12 @@ class _SCCEBase:
         self.log_to_files = True
         self._pending = []
 
+    _fused = None      # set by QuantBank.forward for the duration of one training step (value + workspace of this term)
+
     def _penalty(self):
+        fused, self._fused = self._fused, None
+        if fused is not None:
+            return _PenaltyFromForward.apply(self._kind, fused, *_layer_tensors(self.layers))
         return _Penalty.apply(self._kind, *_layer_tensors(self.layers))
 
     def compute_total_loss(self, y_true, y_pred):

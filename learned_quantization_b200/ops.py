@@ -320,6 +320,29 @@ def penalty_fwd(kind: int, Ps, ss, layouts=None):
     return out, ws
 
 
+def mt_fq_fwd_penalty(kind: int, Ps, ss, ys, layouts=None, ws: Optional[torch.Tensor] = None,
+                      out: Optional[torch.Tensor] = None, round_mode=_lib.LQ_ROUND_FLOOR, qmin=NEG_INF, qmax=POS_INF):
+    """The forward of every tensor and the MaxBin / Difference term over them in one pass (lq_mt_fq_fwd_penalty):
+    ys are written as mt_fq_fwd writes them; returns (scalar, ws) exactly as penalty_fwd does, for penalty_bwd.
+    ws / out may be passed in (static buffers of a captured training step)."""
+    _require_cuda(*Ps, *ss, *ys)
+    layouts = layouts or [tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
+    if any(not same_layout(y, p) for y, p in zip(ys, Ps)):
+        raise ValueError("every y must be laid out in memory like its P")
+    arr = desc_array([make_desc(P=p, s=s, y=y, layout=l) for p, s, y, l in zip(Ps, ss, ys, layouts)])
+    need = max(workspace_bytes(arr, _lib.LQ_PHASE_PENALTY_FWD), 256)
+    if ws is None:
+        ws = torch.empty(need, dtype=torch.uint8, device=Ps[0].device)          # kept for the backward
+    elif ws.numel() < need:
+        raise ValueError(f"workspace of {need} bytes needed, got {ws.numel()}")
+    if out is None:
+        out = torch.empty((), dtype=torch.float32, device=Ps[0].device)
+    with torch.cuda.device(Ps[0].device):
+        check(lib.lq_mt_fq_fwd_penalty(kind, arr, len(arr), round_mode, qmin, qmax, out.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream()))
+    return out, ws
+
+
 def penalty_bwd(kind: int, Ps, ss, ws: torch.Tensor, upstream: float = 1.0,
                 upstream_dev: Optional[torch.Tensor] = None, layouts=None, dXs=None, dss=None,
                 accumulate: bool = False):

@@ -15,6 +15,8 @@ constraint ops.  Here:
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, List, Optional
 
 import torch
@@ -69,11 +71,46 @@ class QuantBank:
             self.ys.append(y.requires_grad_(True))
             off += -(-p.numel() // 4) * 4
 
+    def fuse_loss(self, loss) -> bool:
+        """Let the forward produce the MaxBin / Difference term of `loss` (an SCCE* object of custom_loss_functions) as a
+        by-product of the same pass (lq_mt_fq_fwd_penalty, SURVEY 8b / 8d: "penalty forward fused into K1").  Possible when
+        every tensor the loss walks (LF:85-88: kernel and bias of each layer, with their scales) is one of the bank's."""
+        from ..custom_loss_terms.custom_components import custom_loss_functions as lf
+        if getattr(loss, "_kind", None) not in (_lib.LQ_PEN_MAXBIN, _lib.LQ_PEN_DIFFERENCE):
+            return False
+        tensors = lf._layer_tensors(loss.layers)
+        where = {id(p): i for i, p in enumerate(self.params)}
+        idx = []
+        for p, s in zip(tensors[0::2], tensors[1::2]):
+            i = where.get(id(p))
+            if i is None or self.scales[i] is not s:
+                return False
+            idx.append(i)
+        if len(set(idx)) != len(idx):
+            return False
+        rest = [i for i in range(len(self.params)) if i not in set(idx)]
+        self._fused = {"loss": loss, "idx": idx, "rest": rest, "ws": None,
+                       "out": torch.empty((), dtype=torch.float32, device=self.params[0].device)}
+        return True
+
+    _fused = None
+
     def forward(self) -> None:
         """ONE launch: y_i = floor(P_i / s_i) * s_i for every tensor; layers then hand out y_i."""
         with torch.no_grad():
-            ops.mt_fq_fwd([p.data for p in self.params], [s.data for s in self.scales],
-                          [y.data for y in self.ys], self.layouts)
+            f = self._fused
+            if f is None:
+                ops.mt_fq_fwd([p.data for p in self.params], [s.data for s in self.scales],
+                              [y.data for y in self.ys], self.layouts)
+            else:
+                # the loss's tensors, in the loss's order: forward + loss term in one pass; whatever else is quantised after
+                pick = lambda idx: ([self.params[i].data for i in idx], [self.scales[i].data for i in idx],
+                                    [self.ys[i].data for i in idx], [self.layouts[i] for i in idx])
+                Ps, ss, ys, layouts = pick(f["idx"])
+                out, f["ws"] = ops.mt_fq_fwd_penalty(f["loss"]._kind, Ps, ss, ys, layouts, ws=f["ws"], out=f["out"])
+                if f["rest"]:
+                    ops.mt_fq_fwd(*pick(f["rest"]))
+                f["loss"]._fused = {"out": out, "ws": f["ws"], "Ps": Ps, "ss": ss, "layouts": layouts}
         for q, y in zip(self.qlayers, self.ys):
             y.grad = None
             q._banked = y
@@ -81,6 +118,8 @@ class QuantBank:
     def release(self) -> None:
         for q in self.qlayers:
             q._banked = None
+        if self._fused is not None:
+            self._fused["loss"]._fused = None      # the fused term, too, is valid for this step's parameters only
 
     def backward(self, dys: List[torch.Tensor], dss: List[torch.Tensor]) -> None:
         """dss_i <- scale gradient from dys_i (the parameter gradient is dys_i itself, NQ:118)."""
@@ -98,7 +137,8 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, loss_fn: Callable, *, optimizer: str = "adam", lr: float = 1e-4,
                  momentum: float = 0.0, nesterov: bool = False, weight_decay: float = 0.0,
-                 comm: Optional[Comm] = None, ds_mode: str = "exact", overlap: bool = True, late_blocks: int = 16):
+                 comm: Optional[Comm] = None, ds_mode: str = "exact", overlap: bool = True, late_blocks: int = 16,
+                 fuse_loss: bool = True):
         """overlap (PeerComm, exact mode): start exchanging the late layers' gradients on a side stream as soon
         as the backward has produced them, while it is still working on the early layers.  late_blocks: grid of
         that early-started exchange -- it waits on NVLink, not on arithmetic, so it is given few SMs and a long
@@ -109,6 +149,11 @@ class TrainStep:
         self.ds_mode = ds_mode
         self.bank = QuantBank(model)
         b = self.bank
+        # a custom-loss object (SCCEMaxBin / SCCEDifference bound method): its term comes out of the forward pass itself
+        self._loss_obj = getattr(loss_fn, "__self__", None)
+        self.fused_loss = bool(fuse_loss and not os.environ.get("LQ_NO_FUSE_LOSS")      # (A/B switch for bench runs)
+                               and self._loss_obj is not None and hasattr(self._loss_obj, "_kind")
+                               and b.fuse_loss(self._loss_obj))
         quant_ids = {id(p) for p in b.params} | {id(s) for s in b.scales}
         self.plain = [p for p in model.parameters() if id(p) not in quant_ids and p.requires_grad]
         dev = b.params[0].device

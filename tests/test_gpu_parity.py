@@ -718,6 +718,49 @@ def test_penalties_interleaved_lean_kernels(lq, shape):
         assert rel_err(o1, o2) < TOL and ds_err(s1, s2) <= TOL, kind
 
 
+@pytest.mark.parametrize("round_mode,clamp", [(0, None), (1, (-7.0, 7.0))])
+def test_forward_with_loss_term_equals_the_two_passes(lq, round_mode, clamp):
+    """lq_mt_fq_fwd_penalty (the penalty forward fused into K1): y has the bits lq_mt_fq_fwd writes, the
+    term equals lq_penalty_fwd's, and the workspace it leaves drives lq_penalty_bwd to the same gradients -- ROW and
+    interleaved tensors, odd sizes, an unaligned tensor, zeros and a non-fast scale, more tensors than one table holds."""
+    from learned_quantization_b200 import _lib
+    ops = lq.ops
+    rng = np.random.default_rng(77)
+    shapes = [((3, 3, 64, 128), (1, 1, 64, 1)), ((7, 7, 3, 64), (1, 1, 1, 64)), ((784, 128), (1, 128)), ((128,), (1,)),
+              ((37, 5, 131), (1, 5, 1)), ((9, 6, 4100), (1, 6, 1)), ((5000, 132), (1, 132)), ((513, 7, 2), (1, 7, 1))]
+    shapes += [((64 + i, 24), (1, 24)) for i in range(50)]                 # > kMaxMT tensors: two rounds
+    Ps, ss = [], []
+    for sh, ssh in shapes:
+        P = rng.normal(0, 0.05, size=sh).astype(np.float32)
+        P.reshape(-1)[::19] = 0.0
+        s = rng.uniform(5e-3, 2e-2, size=ssh).astype(np.float32)
+        Ps.append(dev(P)); ss.append(dev(s))
+    ss[2][0, 5] = 1.0                                                      # outside Difference's fast set
+    buf = torch.empty(Ps[4].numel() + 1, device="cuda")                     # a tensor that is not 16-byte aligned
+    buf[1:].copy_(Ps[4].reshape(-1))
+    Ps[4] = buf[1:].view(shapes[4][0])
+    kw = dict(round_mode=round_mode)
+    if clamp:
+        kw.update(qmin=clamp[0], qmax=clamp[1])
+    ys_ref = [torch.empty_like(p) for p in Ps]
+    ops.mt_fq_fwd(Ps, ss, ys_ref, **kw)
+    for kind in (_lib.LQ_PEN_MAXBIN, _lib.LQ_PEN_DIFFERENCE):
+        out_ref, ws_ref = ops.penalty_fwd(kind, Ps, ss)
+        ys = [torch.full_like(p, float("nan")) for p in Ps]
+        out, ws = ops.mt_fq_fwd_penalty(kind, Ps, ss, ys, **kw)
+        for y, yr in zip(ys, ys_ref):
+            assert bits_equal(host(y), host(yr)), kind
+        assert rel_err(host(out), host(out_ref)) < TOL, kind
+        dXs, dss = ops.penalty_bwd(kind, Ps, ss, ws, 0.5)
+        dXr, dsr = ops.penalty_bwd(kind, Ps, ss, ws_ref, 0.5)
+        for a, b in zip(dXs, dXr):
+            assert bits_equal(host(a), host(b)), kind
+        for a, b in zip(dss, dsr):
+            assert ds_err(host(a), host(b)) <= TOL, kind
+    with pytest.raises(lq._lib.LqError):                                    # Inverse reads no tensor
+        ops.mt_fq_fwd_penalty(_lib.LQ_PEN_INVERSE, Ps, ss, [torch.empty_like(p) for p in Ps])
+
+
 def test_penalties_many_tensors_and_a_huge_group(lq):
     """More tensors than one kernel-parameter table holds (the scalar stage chains over launches) and a
     per-tensor scale on a 9.4 M-element kernel (more than 4096 partials: the two-level fold)."""

@@ -320,15 +320,24 @@ def test_custom_loss_variant_step_equals_per_layer_autograd(lq, cls_name, tmp_pa
         p.grad = None
     loss_obj.compute_total_loss(y, net(x)).mean().backward()
     ref = {id(p): (None if p.grad is None else p.grad.clone()) for p in net.parameters()}
-    step = TrainStep(net, loss_obj.compute_total_loss, optimizer="sgd", lr=0.0)     # lr 0: parameters stay put
-    step(x, y)
-    b = step.bucket
-    for v, p in list(zip(b.dy, step.bank.params)) + list(zip(b.ds, step.bank.scales)):
-        r = ref[id(p)]
-        r = torch.zeros_like(p) if r is None else r
-        a, rr = v.cpu().numpy().reshape(-1), r.cpu().numpy().reshape(-1)
-        assert float(np.max(np.abs(a - rr))) <= 1e-4 * max(float(np.max(np.abs(rr))), 1e-30), (cls_name, tuple(p.shape))
-    assert any(float(v.abs().max()) > 0 for v in b.ds), "the loss term must produce scale gradients"
+    # fuse_loss: MaxBin / Difference come out of the step's forward pass as by-products (lq_mt_fq_fwd_penalty); the
+    # stand-alone pass (fuse_loss=False, and always for Inverse) must give the same step
+    for fuse in (True, False):
+        step = TrainStep(net, loss_obj.compute_total_loss, optimizer="sgd", lr=0.0, fuse_loss=fuse)     # lr 0: parameters stay put
+        assert step.fused_loss == (fuse and cls_name != "SCCEInverse")
+        loss = step(x, y)
+        assert loss_obj._fused is None, "the fused term must not outlive its step"
+        b = step.bucket
+        for v, p in list(zip(b.dy, step.bank.params)) + list(zip(b.ds, step.bank.scales)):
+            r = ref[id(p)]
+            r = torch.zeros_like(p) if r is None else r
+            a, rr = v.cpu().numpy().reshape(-1), r.cpu().numpy().reshape(-1)
+            assert float(np.max(np.abs(a - rr))) <= 1e-4 * max(float(np.max(np.abs(rr))), 1e-30), (cls_name, fuse, tuple(p.shape))
+        assert any(float(v.abs().max()) > 0 for v in b.ds), "the loss term must produce scale gradients"
+        if fuse:
+            loss_fused = float(loss)
+        else:
+            assert abs(float(loss) - loss_fused) <= 1e-6 * abs(loss_fused)
 
 
 def test_paper_variant_step_with_sgd_nesterov(lq):
