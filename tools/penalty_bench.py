@@ -42,10 +42,18 @@ def main():
     quick = os.environ.get("PEN_QUICK")          # A/B runs: the three 64 Mi layouts, forward passes of MaxBin / Difference
     cases["imagenette_inventory"] = [(k, ops.scale_shape(k, "channelwise")) for k in mb.KERNELS] + \
                                     [((k[-1],), (1,)) for k in mb.KERNELS]
+    # the same inventory with the conv kernels stored O,H,W,I in memory (logical HWIO): what the training step holds
+    cases["imagenette_inventory_ohwi"] = cases["imagenette_inventory"]
     if quick:
         cases.pop("imagenette_inventory")
+        cases.pop("imagenette_inventory_ohwi")
     for name, shapes in cases.items():
-        Ps = [torch.empty(s, device="cuda").normal_(0, 0.05, generator=g) for s, _ in shapes]
+        if name.endswith("_ohwi"):
+            Ps = [torch.empty((s[3], s[0], s[1], s[2]) if len(s) == 4 else s, device="cuda").normal_(0, 0.05, generator=g)
+                  for s, _ in shapes]
+            Ps = [p.permute(1, 2, 3, 0) if p.dim() == 4 else p for p in Ps]
+        else:
+            Ps = [torch.empty(s, device="cuda").normal_(0, 0.05, generator=g) for s, _ in shapes]
         ss = [torch.empty(t, device="cuda").uniform_(5e-3, 2e-2, generator=g) for _, t in shapes]
         n = sum(p.numel() for p in Ps)
         dXs = [torch.empty_like(p) for p in Ps]
