@@ -9,19 +9,34 @@
 
 namespace lq {
 
-constexpr int kCsRowsPerBlock = 256;
+// Rows per block: the grid is held to ~4 blocks per SM -- the second stage walks the chunks, and with a fixed 256 rows per
+// block the IMAGENETTE step's first layer ([802816, 64]) left it 3136 partial rows to add with two blocks (41 us), while its
+// last layers ([3136, 512]) ran the first stage on 13 blocks (8.5 us for 6.4 MB).  Never fewer than 16 rows per block.
+constexpr long long kCsTargetBlocks = 148 * 4;
+constexpr long long kCsMinRows = 16;
+inline long long colsum_rows_per_block(long long rows, long long ncolblk) {
+  long long target = kCsTargetBlocks / (ncolblk > 0 ? ncolblk : 1);
+  if (target < 1) target = 1;
+  long long rpb = (rows + target - 1) / target;
+  return rpb < kCsMinRows ? kCsMinRows : rpb;
+}
+inline long long colsum_ncolblk(long long cols, bool vec) {
+  const long long ncv = vec ? cols / 4 : cols;
+  const long long bx = ncv < 256 ? ncv : 256;
+  return bx > 0 ? (ncv + bx - 1) / bx : 1;
+}
 
 // grid (nchunks, ncolblk); block 256 = bx column-vectors x by rows
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, long long rows, long long cols,
-                                                             int bx, int by, int vec, float* __restrict__ part) {
+                                                             int bx, int by, int vec, long long rpb, float* __restrict__ part) {
   cudaGridDependencySynchronize();
   __shared__ float4 sm[256];
   const int t = threadIdx.x, ty = t / bx, tx = t - ty * bx;
   const long long cv = (long long)blockIdx.y * bx + tx;
   const long long ncv = vec ? cols / 4 : cols;
   const bool active = ty < by && cv < ncv;
-  const long long r0 = (long long)blockIdx.x * kCsRowsPerBlock;
-  const long long r1 = (r0 + kCsRowsPerBlock < rows) ? r0 + kCsRowsPerBlock : rows;
+  const long long r0 = (long long)blockIdx.x * rpb;
+  const long long r1 = (r0 + rpb < rows) ? r0 + rpb : rows;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     if (vec) {
@@ -62,21 +77,31 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, long long nchunks, long long cols,
-                                                           float* __restrict__ out) {
+// Second stage: lanes are adjacent columns (coalesced), the block's 32 warps split the chunks, four loads in flight each;
+// warp w adds chunks w, w + 32, ... in order, the warps' sums are added in warp order: deterministic, fp64 throughout.
+constexpr int kCsFinalWarps = 32;
+__global__ void __launch_bounds__(32 * kCsFinalWarps) colsum_final_kernel(const float* __restrict__ part, long long nchunks, long long cols,
+                                                                          float* __restrict__ out) {
   cudaGridDependencySynchronize();
-  const long long c = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
-  const int w = threadIdx.x >> 5;          // 8 warps split the chunks; lanes are adjacent columns (coalesced)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long c = (long long)blockIdx.x * 32 + lane;
   double acc = 0.0;
-  if (c < cols)
-    for (long long k = w; k < nchunks; k += 8) acc += (double)part[k * cols + c];
-  __shared__ double sm[8][33];
-  sm[w][threadIdx.x & 31] = acc;
+  if (c < cols) {
+    long long k = w;
+    for (; k + 3 * kCsFinalWarps < nchunks; k += 4 * kCsFinalWarps) {
+      const float a0 = part[k * cols + c], a1 = part[(k + kCsFinalWarps) * cols + c];
+      const float a2 = part[(k + 2 * kCsFinalWarps) * cols + c], a3 = part[(k + 3 * kCsFinalWarps) * cols + c];
+      acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
+    }
+    for (; k < nchunks; k += kCsFinalWarps) acc += (double)part[k * cols + c];
+  }
+  __shared__ double sm[kCsFinalWarps][33];
+  sm[w][lane] = acc;
   __syncthreads();
   if (w == 0 && c < cols) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += sm[i][threadIdx.x];
+    for (int i = 0; i < kCsFinalWarps; ++i) s += sm[i][lane];
     out[c] = (float)s;
   }
 }
@@ -88,7 +113,15 @@ using namespace lq;
 extern "C" int lq_colsum_workspace_bytes(int64_t rows, int64_t cols, size_t* out_bytes) {
   if (!out_bytes) { set_error("lq_colsum_workspace_bytes: null out"); return LQ_E_NULLPTR; }
   if (rows < 0 || cols < 0) { set_error("lq_colsum_workspace_bytes: negative size"); return LQ_E_BADSHAPE; }
-  *out_bytes = align256((size_t)((rows + kCsRowsPerBlock - 1) / kCsRowsPerBlock) * (size_t)cols * sizeof(float));
+  // whichever form runs (the vector form needs an aligned pointer, unknown here): the larger chunk count of the two
+  long long nchunks = 0;
+  for (int vec = 0; vec < 2; ++vec) {
+    if (vec && cols % 4 != 0) continue;
+    const long long rpb = colsum_rows_per_block(rows, colsum_ncolblk(cols, vec != 0));
+    const long long n = (rows + rpb - 1) / rpb;
+    if (n > nchunks) nchunks = n;
+  }
+  *out_bytes = align256((size_t)nchunks * (size_t)cols * sizeof(float));
   return LQ_OK;
 }
 
@@ -99,20 +132,21 @@ extern "C" int lq_colsum(const float* x, int64_t rows, int64_t cols, float* out,
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return cuda_fail(cudaMemsetAsync(out, 0, (size_t)cols * 4, st), "lq_colsum: zero");
   if (!x) { set_error("lq_colsum: null x"); return LQ_E_NULLPTR; }
-  const long long nchunks = (rows + kCsRowsPerBlock - 1) / kCsRowsPerBlock;
-  const size_t need = align256((size_t)nchunks * (size_t)cols * sizeof(float));
-  if (!ws || ws_bytes < need || !aligned16(ws)) { set_error("lq_colsum: workspace %zu B needed, got %zu", need, ws_bytes); return LQ_E_WORKSPACE; }
-  if (nchunks > 0x7fffffffll) { set_error("lq_colsum: too many rows"); return LQ_E_BADSHAPE; }
   const int vec = (aligned16(x) && cols % 4 == 0) ? 1 : 0;
   const long long ncv = vec ? cols / 4 : cols;
   int bx = ncv < 256 ? (int)ncv : 256;
   int by = 256 / bx;
   const long long ncolblk = (ncv + bx - 1) / bx;
   if (ncolblk > 65535) { set_error("lq_colsum: too many columns"); return LQ_E_BADSHAPE; }
+  const long long rpb = colsum_rows_per_block(rows, ncolblk);
+  const long long nchunks = (rows + rpb - 1) / rpb;
+  const size_t need = align256((size_t)nchunks * (size_t)cols * sizeof(float));
+  if (!ws || ws_bytes < need || !aligned16(ws)) { set_error("lq_colsum: workspace %zu B needed, got %zu", need, ws_bytes); return LQ_E_WORKSPACE; }
+  if (nchunks > 0x7fffffffll) { set_error("lq_colsum: too many rows"); return LQ_E_BADSHAPE; }
   float* part = static_cast<float*>(ws);
   int rc = launch_after(colsum_partial_kernel, dim3((unsigned)nchunks, (unsigned)ncolblk), dim3(256), st, "colsum launch",
-                        x, (long long)rows, (long long)cols, bx, by, vec, part);
+                        x, (long long)rows, (long long)cols, bx, by, vec, rpb, part);
   if (rc) return rc;
-  return launch_after(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(256), st, "colsum final launch",
+  return launch_after(colsum_final_kernel, dim3((unsigned)((cols + 31) / 32)), dim3(32 * kCsFinalWarps), st, "colsum final launch",
                       (const float*)part, nchunks, (long long)cols, out);
 }

@@ -294,11 +294,15 @@ FinJob make_fin(const Geom& g, const float4* part, float* ds, const float* s, fl
 
 // The forward writes no partials, so its COL row chunks need not be the backward's: short-lived blocks (a few trips
 // per thread) leave a finer tail at the end of the grid.  Only the block count changes; vector forms only.
-Geom fwd_geom(long long outer, long long C, long long inner, bool al) {
+// min_rpc: a multi-tensor launch's share-based chunk (mt_col_rpc below), which wins over the short chunks.
+Geom fwd_geom(long long outer, long long C, long long inner, bool al, long long min_rpc = 0) {
   Geom g = make_geom(outer, C, inner, al);
-  if (LQ_COL_FWD_TRIPS > 0 && g.regime == REG_COL && g.vec_ok) {
-    long long rpc = (long long)g.by * LQ_COL_U1 * LQ_COL_FWD_TRIPS;
-    if (rpc < g.rpc) {
+  if (g.regime == REG_COL && g.vec_ok) {
+    long long rpc = g.rpc;
+    if (LQ_COL_FWD_TRIPS > 0 && (long long)g.by * LQ_COL_U1 * LQ_COL_FWD_TRIPS < rpc) rpc = (long long)g.by * LQ_COL_U1 * LQ_COL_FWD_TRIPS;
+    if (min_rpc > rpc) rpc = min_rpc;
+    if (rpc > g.outer) rpc = g.outer;
+    if (rpc != g.rpc) {
       g.rpc = (int)rpc;
       g.nchunks = cdiv(g.outer, rpc);
       g.nblocks = g.nchunks * g.ncolblk;
@@ -565,12 +569,16 @@ extern "C" int lq_mt_fq_fwd(const lq_tensor_desc* descs, int n, int round_mode, 
   cudaStream_t st = (cudaStream_t)stream;
   for (int i0 = 0; i0 < n; i0 += kMaxMT) {
     JobTable tab{};
-    for (int i = i0; i < n && i < i0 + kMaxMT; ++i) {
+    const int i1 = (i0 + kMaxMT < n) ? i0 + kMaxMT : n;
+    for (int i = i0; i < i1; ++i)
+      if ((rc = check_dims(descs[i].outer, descs[i].C, descs[i].inner))) return rc;
+    long long share_rpc[kMaxMT];
+    mt_col_rpc(descs, i0, i1, LQ_COL_U1, true, share_rpc);
+    for (int i = i0; i < i1; ++i) {
       const lq_tensor_desc& d = descs[i];
-      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
       if (d.outer * d.C * d.inner == 0) continue;
       if (!d.P || !d.s || !d.y) { set_error("lq_mt_fq_fwd: desc %d has null P/s/y", i); return LQ_E_NULLPTR; }
-      Geom g = fwd_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.y));
+      Geom g = fwd_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.y), share_rpc[i - i0]);
       if ((rc = check_blocks(g))) return rc;
       tab.job[tab.n++] = make_job(g, d.P, d.s, nullptr, d.y, nullptr, nullptr, 0, nullptr);
     }
@@ -620,14 +628,18 @@ extern "C" int lq_mt_fq_bwd(const lq_tensor_desc* descs, int n, float penalty_th
     JobTable tab{};
     FinTable fin{};
     unsigned groups = 0;
-    for (int i = i0; i < n && i < i0 + kMaxMT; ++i) {
+    const int i1 = (i0 + kMaxMT < n) ? i0 + kMaxMT : n;
+    for (int i = i0; i < i1; ++i)
+      if ((rc = check_dims(descs[i].outer, descs[i].C, descs[i].inner))) return rc;
+    long long share_rpc[kMaxMT];
+    mt_col_rpc(descs, i0, i1, 8, false, share_rpc);            // run_col1: one column per thread, eight rows per trip
+    for (int i = i0; i < i1; ++i) {
       const lq_tensor_desc& d = descs[i];
-      if ((rc = check_dims(d.outer, d.C, d.inner))) return rc;
       if (d.outer * d.C * d.inner == 0) continue;
       if (!d.P || !d.s || !d.dy || !d.ds) { set_error("lq_mt_fq_bwd: desc %d has null P/s/dy/ds", i); return LQ_E_NULLPTR; }
       const bool wr = (d.dX != nullptr && d.dX != d.dy);
       Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dy) && (!wr || aligned16(d.dX)) &&
-                                                d.inner >= kRowMinInner);
+                                                d.inner >= kRowMinInner, (int)share_rpc[i - i0]);
       if ((rc = check_blocks(g))) return rc;
       const size_t need = align256((size_t)g.npartials * sizeof(float4));
       if (!ws || off + need > ws_bytes) {

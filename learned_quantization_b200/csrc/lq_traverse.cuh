@@ -601,6 +601,35 @@ int launch_job(const Job& j, const Op& op, cudaStream_t st) {
   return cuda_fail(cudaGetLastError(), "kernel launch");
 }
 
+// Row chunks of the interleaved (COL) tensors of ONE multi-tensor launch.  make_geom's rule gives every tensor enough
+// blocks to fill the GPU by itself (~4 per SM); with the 40 tensors of a model in one launch that made 2700-3700 blocks
+// of 8 rows each (16 KB of work behind a prologue of four reciprocals per thread): 29 us forward / 38 us backward for
+// 45 MB that sit in L2.  Here the launch as a whole gets ~8 blocks per SM and a tensor its share by size; a tensor never
+// gets shorter chunks than make_geom's (a launch of one large tensor is unchanged).  rpc[i - i0] = 0: keep the default.
+// The workspace is sized for the default geometry (lq_workspace_bytes), an upper bound: longer chunks, fewer partials.
+inline void mt_col_rpc(const lq_tensor_desc* descs, int i0, int i1, int rows_per_trip, bool vec_form, long long* rpc) {
+  double n_col = 0.0;
+  for (int i = i0; i < i1; ++i) {
+    rpc[i - i0] = 0;
+    const lq_tensor_desc& d = descs[i];
+    if (d.outer <= 0 || d.C <= 1 || d.inner <= 0 || d.inner >= kRowMinInner) continue;
+    n_col += (double)d.outer * (double)d.C * (double)d.inner;
+  }
+  if (n_col == 0.0) return;
+  for (int i = i0; i < i1; ++i) {
+    const lq_tensor_desc& d = descs[i];
+    if (d.outer <= 0 || d.C <= 1 || d.inner <= 0 || d.inner >= kRowMinInner) continue;
+    const Geom g = make_geom(d.outer, d.C, d.inner, vec_form);      // bx / by / ncolblk of the form that will run
+    if (g.regime != REG_COL) continue;
+    const double n = (double)d.outer * (double)d.C * (double)d.inner;
+    long long target = (long long)(148.0 * 8.0 * n / n_col);
+    if (target < 1) target = 1;
+    const long long trip = (long long)g.by * rows_per_trip;
+    long long r = cdiv(cdiv(d.outer * g.ncolblk, target), trip) * trip;
+    if (r > g.rpc) rpc[i - i0] = r;
+  }
+}
+
 template <class Op>
 int launch_mt(JobTable& tab, const Op& op, cudaStream_t st) {
   JobTable part;

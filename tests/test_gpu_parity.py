@@ -534,7 +534,12 @@ def test_multi_tensor_equals_single(lq):
     for p, s, dy, y, ds in zip(Ps, ss, dys, ys, dss):
         y1 = ops.fq_fwd(p, s)
         _, ds1 = ops.fq_bwd_threshold(dy, p, s, 1e-3)
-        assert bits_equal(host(y), host(y1)) and bits_equal(host(ds), host(ds1))
+        # y: same bits.  ds: the multi-tensor launch cuts interleaved tensors into longer row chunks than a launch of the
+        # tensor by itself would (a share of ONE grid instead of a grid each), so the partials are added in another order
+        assert bits_equal(host(y), host(y1)) and ds_close(host(ds).reshape(-1), host(ds1).reshape(-1))
+    dss_b = [torch.empty_like(s) for s in ss]
+    ops.mt_fq_bwd(dys, Ps, ss, dss_b, 1e-3)
+    assert all(bits_equal(host(a), host(b)) for a, b in zip(dss, dss_b)), "the multi-tensor backward must be deterministic"
     dss0 = [torch.ones_like(s) for s in ss]
     from learned_quantization_b200 import _lib
     ops.mt_fq_bwd(dys, Ps, ss, dss0, 1e-3, scale_grad_mode=_lib.LQ_SGRAD_NONE)
