@@ -1240,7 +1240,8 @@ static int pen_fold_large(FinTable& fin, cudaStream_t st) {
 #ifndef LQ_STAT_BPS
 #define LQ_STAT_BPS 8
 #endif
-static Geom make_stat_geom(long long outer, long long C, long long inner, bool aligned) {
+// target: blocks a multi-tensor launch grants this tensor (mt_col_targets; 0 = a launch of its own): the chunks only grow.
+static Geom make_stat_geom(long long outer, long long C, long long inner, bool aligned, long long target = 0) {
   Geom g = make_geom(outer, C, inner, aligned);
   if (g.regime != REG_COL || !g.vec_ok) return g;
   const int bx = g.ncol < LQ_STAT_BX ? (int)g.ncol : LQ_STAT_BX;
@@ -1249,6 +1250,8 @@ static Geom make_stat_geom(long long outer, long long C, long long inner, bool a
   long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * LQ_STAT_BPS), by) * by;
   if (rpc < by) rpc = by;
   if (rpc > 1024) rpc = 1024 / by * by;
+  const long long shared = share_rpc(outer, ncolblk, target, by);
+  if (shared > rpc && shared > g.rpc) rpc = shared;    // the launch's 40 tensors share one grid (see mt_col_targets)
   if (rpc > outer) rpc = outer;
   if (rpc <= g.rpc) return g;                       // short tensors: the default chunks are already the longer ones
   g.bx = bx; g.by = by; g.rpc = (int)rpc;
@@ -1333,6 +1336,8 @@ static int pen_fwd_impl(const char* who, int kind, const lq_tensor_desc* descs, 
     JobTable tab{}; FinTable fin{}; ScalarTable sc{}; TieTable ties{};
     unsigned groups = 0, tie_blocks = 0;
     sc.kind = kind; sc.first = (i0 == 0); sc.last = (i1 == n); sc.normalizer = nrm;
+    long long target[kMaxMT];
+    mt_col_targets(descs, i0, i1, target);
     for (int i = i0; i < i1; ++i) {
       const lq_tensor_desc& d = descs[i];
       const long long cnt = d.outer * d.C * d.inner;
@@ -1340,7 +1345,7 @@ static int pen_fwd_impl(const char* who, int kind, const lq_tensor_desc* descs, 
       float4* part = reinterpret_cast<float4*>(base + lay[i].part_off);
       float4* gstat = reinterpret_cast<float4*>(base + lay[i].gstat_off);
       if (kind != LQ_PEN_INVERSE) {
-        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && (!fwd || aligned16(d.y)));
+        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && (!fwd || aligned16(d.y)), target[i - i0]);
         if (g.nblocks > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
         Job j = make_job(g, d.P, d.s, nullptr, fwd ? d.y : nullptr, nullptr, nullptr, 0, part);
         j.gaux = gstat;                                           // pen_ties_kernel: the group's {max, ties, -, lo}
@@ -1434,6 +1439,8 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
     JobTable tab{}; FinTable fin{}; GroupTable gt{};
     unsigned groups = 0;
     gt.kind = kind;
+    long long target[kMaxMT];
+    mt_col_targets(descs, i0, i1, target);               // the forward's cut of every tensor, again
     for (int i = i0; i < i1; ++i) {
       const lq_tensor_desc& d = descs[i];
       const long long cnt = d.outer * d.C * d.inner;
@@ -1446,7 +1453,7 @@ extern "C" int lq_penalty_bwd(int kind, const lq_tensor_desc* descs, int n, floa
         gt.job[gt.n++] = gj;
       }
       if (kind != LQ_PEN_INVERSE) {
-        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dX));   // the forward's cut of the tensor
+        Geom g = make_stat_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(d.dX), target[i - i0]);   // the forward's cut of the tensor
         if (g.nblocks > 0x7fffffffll) { rc = LQ_E_BADSHAPE; set_error("tensor too large"); break; }
         Job j = make_job(g, d.P, d.s, d.dX, nullptr, d.dX, nullptr, 0, part);
         j.write_dx = 1;

@@ -607,25 +607,37 @@ int launch_job(const Job& j, const Op& op, cudaStream_t st) {
 // 45 MB that sit in L2.  Here the launch as a whole gets ~8 blocks per SM and a tensor its share by size; a tensor never
 // gets shorter chunks than make_geom's (a launch of one large tensor is unchanged).  rpc[i - i0] = 0: keep the default.
 // The workspace is sized for the default geometry (lq_workspace_bytes), an upper bound: longer chunks, fewer partials.
-inline void mt_col_rpc(const lq_tensor_desc* descs, int i0, int i1, int rows_per_trip, bool vec_form, long long* rpc) {
+// target[i - i0] = blocks the launch's budget (~8 per SM) grants interleaved tensor i by its size; 0 = not such a tensor
+inline void mt_col_targets(const lq_tensor_desc* descs, int i0, int i1, long long* target) {
   double n_col = 0.0;
+  auto is_col = [](const lq_tensor_desc& d) { return d.outer > 0 && d.C > 1 && d.inner > 0 && d.inner < kRowMinInner; };
   for (int i = i0; i < i1; ++i) {
-    rpc[i - i0] = 0;
-    const lq_tensor_desc& d = descs[i];
-    if (d.outer <= 0 || d.C <= 1 || d.inner <= 0 || d.inner >= kRowMinInner) continue;
-    n_col += (double)d.outer * (double)d.C * (double)d.inner;
+    target[i - i0] = 0;
+    if (is_col(descs[i])) n_col += (double)descs[i].outer * (double)descs[i].C * (double)descs[i].inner;
   }
   if (n_col == 0.0) return;
   for (int i = i0; i < i1; ++i) {
+    if (!is_col(descs[i])) continue;
+    const double n = (double)descs[i].outer * (double)descs[i].C * (double)descs[i].inner;
+    const long long t = (long long)(148.0 * 8.0 * n / n_col);
+    target[i - i0] = t < 1 ? 1 : t;
+  }
+}
+// the row chunk that gives a tensor of `outer` rows and `ncolblk` column blocks about `target` blocks, a multiple of `round_to`
+inline long long share_rpc(long long outer, long long ncolblk, long long target, long long round_to) {
+  if (target <= 0) return 0;
+  return cdiv(cdiv(outer * ncolblk, target), round_to) * round_to;
+}
+inline void mt_col_rpc(const lq_tensor_desc* descs, int i0, int i1, int rows_per_trip, bool vec_form, long long* rpc) {
+  long long target[kMaxMT];
+  mt_col_targets(descs, i0, i1, target);
+  for (int i = i0; i < i1; ++i) {
+    rpc[i - i0] = 0;
+    if (target[i - i0] == 0) continue;
     const lq_tensor_desc& d = descs[i];
-    if (d.outer <= 0 || d.C <= 1 || d.inner <= 0 || d.inner >= kRowMinInner) continue;
     const Geom g = make_geom(d.outer, d.C, d.inner, vec_form);      // bx / by / ncolblk of the form that will run
     if (g.regime != REG_COL) continue;
-    const double n = (double)d.outer * (double)d.C * (double)d.inner;
-    long long target = (long long)(148.0 * 8.0 * n / n_col);
-    if (target < 1) target = 1;
-    const long long trip = (long long)g.by * rows_per_trip;
-    long long r = cdiv(cdiv(d.outer * g.ncolblk, target), trip) * trip;
+    const long long r = share_rpc(d.outer, g.ncolblk, target[i - i0], (long long)g.by * rows_per_trip);
     if (r > g.rpc) rpc[i - i0] = r;
   }
 }
