@@ -604,10 +604,14 @@ int launch_job(const Job& j, const Op& op, cudaStream_t st) {
 // Row chunks of the interleaved (COL) tensors of ONE multi-tensor launch.  make_geom's rule gives every tensor enough
 // blocks to fill the GPU by itself (~4 per SM); with the 40 tensors of a model in one launch that made 2700-3700 blocks
 // of 8 rows each (16 KB of work behind a prologue of four reciprocals per thread): 29 us forward / 38 us backward for
-// 45 MB that sit in L2.  Here the launch as a whole gets ~8 blocks per SM and a tensor its share by size; a tensor never
+// 45 MB that sit in L2.  Here the launch as a whole gets ~3 blocks per SM (LQ_MT_BPS) and a tensor its share by size; a tensor never
 // gets shorter chunks than make_geom's (a launch of one large tensor is unchanged).  rpc[i - i0] = 0: keep the default.
 // The workspace is sized for the default geometry (lq_workspace_bytes), an upper bound: longer chunks, fewer partials.
-// target[i - i0] = blocks the launch's budget (~8 per SM) grants interleaved tensor i by its size; 0 = not such a tensor
+#ifndef LQ_MT_BPS
+#define LQ_MT_BPS 3.0
+#endif
+// (3 measured best of 3 / 5 / 8 / 12 / 20 on the 40-tensor inventory: forward 18.0 / 19.3 / 19.5 / 20.6 / 20.5 us)
+// target[i - i0] = blocks the launch's budget (~LQ_MT_BPS per SM) grants interleaved tensor i by its size; 0 = not such a tensor
 inline void mt_col_targets(const lq_tensor_desc* descs, int i0, int i1, long long* target) {
   double n_col = 0.0;
   auto is_col = [](const lq_tensor_desc& d) { return d.outer > 0 && d.C > 1 && d.inner > 0 && d.inner < kRowMinInner; };
@@ -619,7 +623,7 @@ inline void mt_col_targets(const lq_tensor_desc* descs, int i0, int i1, long lon
   for (int i = i0; i < i1; ++i) {
     if (!is_col(descs[i])) continue;
     const double n = (double)descs[i].outer * (double)descs[i].C * (double)descs[i].inner;
-    const long long t = (long long)(148.0 * 8.0 * n / n_col);
+    const long long t = (long long)(148.0 * LQ_MT_BPS * n / n_col);
     target[i - i0] = t < 1 ? 1 : t;
   }
 }

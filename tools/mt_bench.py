@@ -45,17 +45,21 @@ def timeit(fn, reps=20, graph=False):
 def main():
     torch.cuda.set_device(0)
     out = {}
+    ohwi = bool(os.environ.get("MT_OHWI"))        # conv kernels stored O,H,W,I in memory (logical HWIO): the training step's layout
     for orient in ("channelwise", "scalar"):
         Ps, ss = [], []
         for shp in KERNELS:
-            Ps.append(torch.randn(shp, device="cuda") * 0.05)
+            if ohwi:
+                Ps.append((torch.randn((shp[3], shp[0], shp[1], shp[2]), device="cuda") * 0.05).permute(1, 2, 3, 0))
+            else:
+                Ps.append(torch.randn(shp, device="cuda") * 0.05)
             ss.append(torch.empty(ops.scale_shape(shp, orient), device="cuda").uniform_(5e-3, 2e-2))
             Ps.append(torch.randn(shp[-1], device="cuda") * 0.05)
             ss.append(torch.empty(1, device="cuda").uniform_(5e-3, 2e-2))
         ys = [torch.empty_like(p) for p in Ps]
         dys = [torch.randn_like(p) * 1e-3 for p in Ps]
         dss = [torch.empty_like(s) for s in ss]
-        layouts = [ops.group_layout(p.shape, s.shape) for p, s in zip(Ps, ss)]
+        layouts = [ops.tensor_layout(p, s.shape) for p, s in zip(Ps, ss)]
         n = sum(p.numel() for p in Ps)
         lam = 1e-3
 
@@ -72,7 +76,7 @@ def main():
         table = ops.OptimizerTable(Ps + ss, dys + dss, adam=True, min_value=[None] * len(Ps) + [1.19e-5] * len(ss))
         step_dev = torch.ones((), dtype=torch.int64, device="cuda")
         opt = lambda: ops.opt_adam(table, 1e-4, step_dev)
-        r = {"tensors": len(Ps), "elements": n}
+        r = {"tensors": len(Ps), "elements": n, "storage": "ohwi" if ohwi else "hwio"}
         for name, fn in (("fwd_per_tensor", fwd_each), ("fwd_mt", fwd_mt), ("bwd_per_tensor", bwd_each), ("bwd_mt", bwd_mt),
                          ("adam_fused", opt)):
             r[name + "_eager_us"] = timeit(fn, graph=False)
