@@ -1250,7 +1250,7 @@ static Geom make_stat_geom(long long outer, long long C, long long inner, bool a
   long long rpc = cdiv(cdiv(outer * ncolblk, 148ll * LQ_STAT_BPS), by) * by;
   if (rpc < by) rpc = by;
   if (rpc > 1024) rpc = 1024 / by * by;
-  const long long shared = share_rpc(outer, ncolblk, target, by);
+  const long long shared = share_rpc(outer, ncolblk, target, by, (long long)bx * 4);
   if (shared > rpc && shared > g.rpc) rpc = shared;    // the launch's 40 tensors share one grid (see mt_col_targets)
   if (rpc > outer) rpc = outer;
   if (rpc <= g.rpc) return g;                       // short tensors: the default chunks are already the longer ones

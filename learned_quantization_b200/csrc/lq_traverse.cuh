@@ -619,7 +619,9 @@ inline void mt_col_targets(const lq_tensor_desc* descs, int i0, int i1, long lon
     target[i - i0] = 0;
     if (is_col(descs[i])) n_col += (double)descs[i].outer * (double)descs[i].C * (double)descs[i].inner;
   }
-  if (n_col == 0.0) return;
+  int count = 0;
+  for (int i = i0; i < i1; ++i) count += is_col(descs[i]) ? 1 : 0;
+  if (count < 2) return;                              // a tensor by itself keeps the geometry tuned for it
   for (int i = i0; i < i1; ++i) {
     if (!is_col(descs[i])) continue;
     const double n = (double)descs[i].outer * (double)descs[i].C * (double)descs[i].inner;
@@ -627,10 +629,15 @@ inline void mt_col_targets(const lq_tensor_desc* descs, int i0, int i1, long lon
     target[i - i0] = t < 1 ? 1 : t;
   }
 }
-// the row chunk that gives a tensor of `outer` rows and `ncolblk` column blocks about `target` blocks, a multiple of `round_to`
-inline long long share_rpc(long long outer, long long ncolblk, long long target, long long round_to) {
+// the row chunk that gives a tensor of `outer` rows and `ncolblk` column blocks of `cols_per_block` columns about `target`
+// blocks: a multiple of `round_to`, and never more than ~64 Ki elements per block (the rule exists for the small tensors
+// of a model; large ones keep blocks of the size their own geometry was tuned to)
+inline long long share_rpc(long long outer, long long ncolblk, long long target, long long round_to, long long cols_per_block) {
   if (target <= 0) return 0;
-  return cdiv(cdiv(outer * ncolblk, target), round_to) * round_to;
+  long long r = cdiv(cdiv(outer * ncolblk, target), round_to) * round_to;
+  long long cap = (65536 / (cols_per_block > 0 ? cols_per_block : 1)) / round_to * round_to;
+  if (cap < round_to) cap = round_to;
+  return r < cap ? r : cap;
 }
 inline void mt_col_rpc(const lq_tensor_desc* descs, int i0, int i1, int rows_per_trip, bool vec_form, long long* rpc) {
   long long target[kMaxMT];
@@ -641,7 +648,7 @@ inline void mt_col_rpc(const lq_tensor_desc* descs, int i0, int i1, int rows_per
     const lq_tensor_desc& d = descs[i];
     const Geom g = make_geom(d.outer, d.C, d.inner, vec_form);      // bx / by / ncolblk of the form that will run
     if (g.regime != REG_COL) continue;
-    const long long r = share_rpc(d.outer, g.ncolblk, target[i - i0], (long long)g.by * rows_per_trip);
+    const long long r = share_rpc(d.outer, g.ncolblk, target[i - i0], (long long)g.by * rows_per_trip, (long long)g.bx * (g.vec_ok ? 4 : 1));
     if (r > g.rpc) rpc[i - i0] = r;
   }
 }
