@@ -433,8 +433,9 @@ extern "C" int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, 
   };
   for (int i = 0; i < n; ++i)
     if ((rc = check_dims(descs[i].outer, descs[i].C, descs[i].inner))) return rc;
-  long long share_rpc[kMaxMT];
-  mt_col_rpc(descs, 0, n, 8, false, share_rpc);       // the same row chunks as lq_mt_fq_bwd on the same table: same bits
+  // (make_geom's own row chunks here, not the shared grid of lq_mt_fq_bwd: this kernel waits on NVLink, and the many short
+  // blocks are what keeps bytes in flight -- with the shared grid the exchange alone took 0.34 ms instead of 0.22 at N = 8.
+  // The two paths therefore add a group's partials in different orders: same ds within rounding, not the same bits.)
   for (int i = 0; i < n; ++i) {
     const lq_tensor_desc& d = descs[i];
     const long long cnt = d.outer * d.C * d.inner;
@@ -445,7 +446,7 @@ extern "C" int lq_dpx_exchange(lq_dpx_t* x, const lq_tensor_desc* descs, int n, 
     if (!k2) { if ((rc = add_plain(dy, cnt))) return rc; continue; }
     if (!d.P || !d.s || !d.ds) { set_error("lq_dpx_exchange: desc %d has null P/s/ds", i); return LQ_E_NULLPTR; }
     if (!in_arena(x, dy, (size_t)cnt * 4)) { set_error("lq_dpx_exchange: desc %d: dy lies outside the arena", i); return LQ_E_BADSHAPE; }
-    Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(dy) && d.inner >= kRowMinInner, (int)share_rpc[i]);
+    Geom g = make_geom(d.outer, d.C, d.inner, aligned16(d.P) && aligned16(dy) && d.inner >= kRowMinInner);
     if ((rc = check_blocks(g))) return rc;
     const size_t need = align256((size_t)g.npartials * sizeof(float4));
     if (!ws || !aligned16(ws) || off + need > ws_bytes || !in_arena(x, static_cast<char*>(ws) + off, need)) {

@@ -14,6 +14,13 @@ import pytest
 
 from conftest import bits_equal
 
+
+def ds_close(got, ref, tol=1e-5):
+    """per-group relative error with a floor of 1e-6 of the largest group (as tests/test_gpu_parity.py)"""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = max(float(np.max(np.abs(ref))), 1e-30) if ref.size else 1.0
+    return bool(np.all(np.abs(got - ref) <= tol * np.maximum(np.abs(ref), 1e-6 * scale)))
+
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
@@ -139,7 +146,10 @@ def test_fused_exchange_equals_mean_then_single_device_backward(lq, world):
                 for i, n in enumerate(sizes + [N_PLAIN]):
                     assert bits_equal(rk.view(i, n).cpu().numpy(), means[i]), (rep, r, i)
                 for i in range(len(sizes)):
-                    assert bits_equal(dss[r][i].cpu().numpy().ravel(), want_ds[i].ravel()), (rep, r, i)
+                    # the same scale gradient as the single-device backward of the mean (the two cut interleaved tensors into
+                    # row chunks of different lengths: equal within rounding), and the same BITS on every rank
+                    assert ds_close(dss[r][i].cpu().numpy().ravel(), want_ds[i].ravel()), (rep, r, i)
+                    assert bits_equal(dss[r][i].cpu().numpy().ravel(), dss[0][i].cpu().numpy().ravel()), (rep, r, i)
             del keep
     finally:
         torch.cuda.synchronize()
@@ -196,7 +206,10 @@ def test_replayed_from_cuda_graphs(lq):
                 for i, n in enumerate(sizes + [N_PLAIN]):
                     assert bits_equal(rk.view(i, n).cpu().numpy(), means[i]), (rep, r, i)
                 for i in range(len(sizes)):
-                    assert bits_equal(dss[r][i].cpu().numpy().ravel(), want_ds[i].ravel()), (rep, r, i)
+                    # the same scale gradient as the single-device backward of the mean (the two cut interleaved tensors into
+                    # row chunks of different lengths: equal within rounding), and the same BITS on every rank
+                    assert ds_close(dss[r][i].cpu().numpy().ravel(), want_ds[i].ravel()), (rep, r, i)
+                    assert bits_equal(dss[r][i].cpu().numpy().ravel(), dss[0][i].cpu().numpy().ravel()), (rep, r, i)
     finally:
         torch.cuda.synchronize()
         for rk in ranks:
