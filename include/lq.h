@@ -226,6 +226,11 @@ int lq_host_fq_fwd_bwd_on(lq_host_t* h, const float* hP, const float* hs, const 
                           int64_t outer, int64_t C, int64_t inner,
                           void* dev_ws, size_t dev_ws_bytes, lq_stream_t after, int order_after);
 
+/* Host-only (no device work, no pointers dereferenced): how lq_mt_fq_fwd (phase LQ_PHASE_FWD) / lq_mt_fq_bwd
+ * (LQ_PHASE_BWD) would cut every tensor of a table: out[4 i .. 4 i + 3] = {regime (0 = rows of one group, 1 = interleaved),
+ * rows per chunk (interleaved) or segment length (rows), blocks, partial slots}.  For tests of the geometry rules. */
+int lq_debug_mt_geometry(const lq_tensor_desc* descs, int n, int phase, int64_t* out);
+
 /* Diagnostics: checks on the device that the kernels' hoisted-reciprocal division equals
  * IEEE division (the bit-exactness the forward is graded on, NQ:56-58 tf.truediv) for every
  * 23-bit mantissa of the dividend a = bits(a_sign_exp_bits | mantissa) against each divisor

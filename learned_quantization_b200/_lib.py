@@ -78,6 +78,7 @@ SIGNATURES = {
     "lq_opt_adam": (_I, [C.POINTER(OptDesc), _I, _F, _F, _F, _F, _I64, _P, _F, _P, _P]),
     "lq_opt_sgd": (_I, [C.POINTER(OptDesc), _I, _F, _F, _I, _F, _P, _P]),
     "lq_debug_divcheck": (_I, [_P, _I64, C.c_uint32, _P, _P]),
+    "lq_debug_mt_geometry": (_I, [_DESCS, _I, _I, C.POINTER(_I64)]),
     "lq_p2p_create": (_I, [_I, _I, _I64, C.POINTER(_P), _P]),
     "lq_p2p_connect": (_I, [_P, _P]),
     "lq_p2p_buffer": (_I, [_P, C.POINTER(_P)]),

@@ -99,3 +99,47 @@ def test_default_initializer_uses_keras_glorot_fans():
         w = layer._init_weight(shape, None, "cpu").detach()
         assert tuple(w.shape) == shape and float(w.abs().max()) <= limit
         assert float(w.abs().max()) > 0.8 * limit and abs(float(w.mean())) < 0.2 * limit
+
+
+# ------------------------------------------------------------------ geometry of multi-tensor launches (host only)
+def _mt_geometry(layouts, phase):
+    import ctypes as C
+    import learned_quantization_b200 as pkg
+    from learned_quantization_b200 import _lib
+    arr = pkg.ops.desc_array([pkg.ops.make_desc(layout=l) for l in layouts])
+    out = (C.c_int64 * (4 * len(layouts)))()
+    _lib.check(_lib.lib.lq_debug_mt_geometry(arr, len(layouts), phase, out))
+    return [tuple(out[4 * i:4 * i + 4]) for i in range(len(layouts))]
+
+
+IMAGENETTE_OHWI = [(64 * 49, 3, 1)] + [(64 * 9, 64, 1)] * 4 + [(128 * 9, 64, 1)] + [(128 * 9, 128, 1)] * 3 + [(128, 64, 1)] + \
+                  [(256 * 9, 128, 1)] + [(256 * 9, 256, 1)] * 3 + [(256, 128, 1)] + [(512 * 9, 256, 1)] + \
+                  [(512 * 9, 512, 1)] * 3 + [(512, 256, 1)]
+
+
+@pytest.mark.parametrize("phase_name", ["LQ_PHASE_FWD", "LQ_PHASE_BWD"])
+def test_interleaved_tensors_of_a_table_share_one_grid(phase_name):
+    """lq_traverse.cuh mt_col_targets: by itself an interleaved tensor gets enough blocks to fill the GPU; 20 conv kernels
+    (O,H,W,I storage, channelwise scales: all interleaved) in ONE launch must not get 20 times that.  Chunks only grow, so
+    the partials never outgrow the workspace sized for the stand-alone geometry; a block never exceeds 64 Ki elements."""
+    from learned_quantization_b200 import _lib
+    phase = getattr(_lib, phase_name)
+    alone = [_mt_geometry([l], phase)[0] for l in IMAGENETTE_OHWI]
+    table = _mt_geometry(IMAGENETTE_OHWI, phase)
+    assert all(a[0] == 1 and t[0] == 1 for a, t in zip(alone, table))            # all interleaved
+    assert sum(t[2] for t in table) <= 148 * 8 < sum(a[2] for a in alone)        # one shared grid instead of twenty
+    for l, a, t in zip(IMAGENETTE_OHWI, alone, table):
+        if phase == _lib.LQ_PHASE_BWD:
+            assert t[1] >= a[1] and t[3] <= a[3], (l, a, t)                      # longer chunks, fewer partials
+        cols_per_block = min(l[1], 1024 if phase == _lib.LQ_PHASE_FWD else 256)
+        assert t[1] * cols_per_block <= 65536 + cols_per_block * 64, (l, t)      # (one rounding unit of slack)
+    # the biases (rows of one group) and a tensor that is the table's only interleaved one are untouched
+    mixed = [(1, 1, 64), (131072, 512, 1), (1, 1, 512)]
+    assert _mt_geometry(mixed, phase) == [_mt_geometry([l], phase)[0] for l in mixed]
+
+
+def test_mt_geometry_rejects_bad_arguments():
+    import learned_quantization_b200 as pkg
+    from learned_quantization_b200 import _lib
+    with pytest.raises(_lib.LqError):
+        _mt_geometry([(4, 4, 4)], _lib.LQ_PHASE_PENALTY_FWD)
